@@ -1,0 +1,472 @@
+// elementwise.cu — the HBM-bound kernels of the denoiser path: embedders, LayerNorm+modulate,
+// final layer, bf16 casts.  Each is bounded by the HBM roofline; the
+// rules that matter are coalesced 128-bit accesses, one pass over the data, and enough
+// CTAs to cover 148 SMs.
+#include "common.cuh"
+
+namespace ditb200 {
+
+// =============================================================== LayerNorm + modulate
+// One warp per token row.  Lane l owns float4 number l + 32*j (j < NV) of the row, so every
+// warp-level load/store is a contiguous 512-byte segment.  The row stays in registers between
+// the statistics pass and the normalise pass: x is read from HBM exactly once.
+template <int NV, bool kOutBf16>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ scale,
+                                                          int mod_stride, void* __restrict__ out,
+                                                          float* __restrict__ stats, int M, int T,
+                                                          float eps) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = ldg_stream_f4(xr + lane + 32 * j);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) * (1.0f / D);
+  const float rstd = 1.0f / sqrtf(var + eps);
+  if (stats != nullptr && lane == 0) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+  const int b = row / T;
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 h4 = __ldg(sh + lane + 32 * j);
+    const float4 c4 = __ldg(sc + lane + 32 * j);
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * (1.0f + c4.x) + h4.x;
+    o.y = (v[j].y - mean) * rstd * (1.0f + c4.y) + h4.y;
+    o.z = (v[j].z - mean) * rstd * (1.0f + c4.z) + h4.z;
+    o.w = (v[j].w - mean) * rstd * (1.0f + c4.w) + h4.w;
+    if constexpr (kOutBf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * D)[lane + 32 * j] = pk;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[lane + 32 * j] = o;
+    }
+  }
+}
+
+// Any D % 4 == 0: same mapping, row re-read from L1/L2 instead of held in registers.
+template <bool kOutBf16>
+__global__ void __launch_bounds__(256) ln_modulate_generic_kernel(
+    const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, void* __restrict__ out, float* __restrict__ stats, int M, int T, int D,
+    float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const int nv = D >> 2;
+  float s = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = xr[i];
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = xr[i];
+    float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = warp_sum(q) / (float)D;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  if (stats != nullptr && lane == 0) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+  const int b = row / T;
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+  for (int i = lane; i < nv; i += 32) {
+    float4 v = xr[i];
+    const float4 h4 = __ldg(sh + i), c4 = __ldg(sc + i);
+    float4 o;
+    o.x = (v.x - mean) * rstd * (1.0f + c4.x) + h4.x;
+    o.y = (v.y - mean) * rstd * (1.0f + c4.y) + h4.y;
+    o.z = (v.z - mean) * rstd * (1.0f + c4.z) + h4.z;
+    o.w = (v.w - mean) * rstd * (1.0f + c4.w) + h4.w;
+    if constexpr (kOutBf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * D)[i] = pk;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[i] = o;
+    }
+  }
+}
+
+// ================================================================ patch embed + pos
+// grid.x = token groups of kTok tokens; threads run over the hidden dimension so every
+// store to out[token, :] is coalesced.  Patches of the group are staged in shared memory.
+constexpr int kPeTok = 16;
+__global__ void __launch_bounds__(256) patch_embed_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    const float* __restrict__ pos, float* __restrict__ out, int B, int C, int H, int W, int p,
+    int D, int round_bf16) {
+  extern __shared__ float patch[];  // [kPeTok][K]
+  const int Hp = H / p, Wp = W / p, T = Hp * Wp, K = C * p * p;
+  const int M = B * T;
+  const int tok0 = blockIdx.x * kPeTok;
+  for (int idx = threadIdx.x; idx < kPeTok * K; idx += blockDim.x) {
+    const int tt = idx / K, k = idx - tt * K;
+    const int tok = tok0 + tt;
+    float v = 0.f;
+    if (tok < M) {
+      const int b = tok / T, t = tok - b * T;
+      const int hp = t / Wp, wp = t - hp * Wp;
+      const int c = k / (p * p), r = k - c * p * p;
+      const int i = r / p, j = r - i * p;
+      v = x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j];
+      if (round_bf16) v = bf16_round(v);
+    }
+    patch[idx] = v;
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc[kPeTok];
+#pragma unroll
+    for (int tt = 0; tt < kPeTok; ++tt) acc[tt] = 0.f;
+    const float* wr = w + (size_t)d * K;
+    for (int k = 0; k < K; ++k) {
+      float wv = __ldg(wr + k);
+      if (round_bf16) wv = bf16_round(wv);
+#pragma unroll
+      for (int tt = 0; tt < kPeTok; ++tt) acc[tt] = fmaf(wv, patch[tt * K + k], acc[tt]);
+    }
+    float bv = bias[d];
+    if (round_bf16) bv = bf16_round(bv);
+#pragma unroll
+    for (int tt = 0; tt < kPeTok; ++tt) {
+      const int tok = tok0 + tt;
+      if (tok < M) {
+        float r = acc[tt] + bv;
+        if (round_bf16) r = bf16_round(r);
+        const int t = tok % T;
+        out[(size_t)tok * D + d] = r + __ldg(pos + (size_t)t * D + d);
+      }
+    }
+  }
+}
+
+// ============================================================= timestep sinusoid
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out,
+                                          int B, int dim, float neg_log_period) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * dim) return;
+  const int b = idx / dim, j = idx - b * dim;
+  float r = 0.f;
+  if (j < 2 * half) {
+    const int k = (j < half) ? j : j - half;
+    // freqs = exp(-log(P) * arange(half) / half), every op rounded to f32 as torch does
+    const float f = expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)k), (float)half));
+    const float a = __fmul_rn((float)t[b], f);
+    r = (j < half) ? cosf(a) : sinf(a);
+  }
+  out[idx] = r;
+}
+
+// ================================================================== label embed
+__global__ void label_embed_kernel(const int64_t* __restrict__ y, const float* __restrict__ table,
+                                   const float* __restrict__ add, float* __restrict__ out, int B,
+                                   int D, int num_rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, d = idx - b * D;
+  long long row = y[b];
+  if (row < 0) row = 0;
+  if (row >= num_rows) row = num_rows - 1;
+  float v = table[(size_t)row * D + d];
+  if (add != nullptr) v = add[idx] + v;  // c = t + y
+  out[idx] = v;
+}
+
+// ===================================================================== casts
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                 size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 v = *reinterpret_cast<const float4*>(in + i);
+      uint2 pk;
+      pk.x = pack_bf16x2(v.x, v.y);
+      pk.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(out + i) = pk;
+    } else {
+      for (size_t k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+    }
+  }
+}
+
+// ================================================================= final layer
+// CTA = kFlRows token rows.  Phase 1: one warp normalises + modulates two rows into shared
+// memory.  Phase 2: a [kFlRows x NO] mini-GEMM against the (transposed, k-chunked) weight,
+// thread = (row, output) so h reads are warp broadcasts and weight reads are conflict-free.
+// The store does the unpatchify permutation ('nhwpqc->nchpwq') directly into NCHW.
+constexpr int kFlRows = 16;
+constexpr int kFlKc = 64;
+template <int NOW>  // padded outputs / 32
+__global__ void __launch_bounds__(256) final_layer_kernel(
+    const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ out, int M, int T, int D, int p, int Cout, float eps, int round_bf16) {
+  extern __shared__ float smem[];
+  float* h = smem;                         // [kFlRows][D]
+  float* wT = smem + (size_t)kFlRows * D;  // [kFlKc][NOW*32]
+  constexpr int NOP = NOW * 32;
+  const int NO = p * p * Cout;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * kFlRows;
+  const int nv = D >> 2;
+  // ---- phase 1
+  for (int rr = warp; rr < kFlRows; rr += 8) {
+    const int row = row0 + rr;
+    float4* hr = reinterpret_cast<float4*>(h + (size_t)rr * D);
+    if (row >= M) {
+      for (int i = lane; i < nv; i += 32) hr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+    float s = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      float4 v = xr[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      float4 v = xr[i];
+      float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)D + eps);
+    const int b = row / T;
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+    for (int i = lane; i < nv; i += 32) {
+      float4 v = xr[i];
+      const float4 h4 = __ldg(sh + i), c4 = __ldg(sc + i);
+      float4 o;
+      o.x = (v.x - mean) * rstd * (1.0f + c4.x) + h4.x;
+      o.y = (v.y - mean) * rstd * (1.0f + c4.y) + h4.y;
+      o.z = (v.z - mean) * rstd * (1.0f + c4.z) + h4.z;
+      o.w = (v.w - mean) * rstd * (1.0f + c4.w) + h4.w;
+      if (round_bf16) {
+        o.x = bf16_round(o.x);
+        o.y = bf16_round(o.y);
+        o.z = bf16_round(o.z);
+        o.w = bf16_round(o.w);
+      }
+      hr[i] = o;
+    }
+  }
+  // ---- phase 2
+  constexpr int NACC = kFlRows * NOP / 256;  // outputs per thread
+  float acc[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+  for (int k0 = 0; k0 < D; k0 += kFlKc) {
+    __syncthreads();  // h complete (first pass) / previous chunk consumed
+    for (int idx = threadIdx.x; idx < NOP * kFlKc; idx += 256) {
+      const int o = idx / kFlKc, kk = idx - o * kFlKc;
+      float wv = 0.f;
+      if (o < NO && k0 + kk < D) wv = __ldg(w + (size_t)o * D + k0 + kk);
+      if (round_bf16) wv = bf16_round(wv);
+      wT[kk * NOP + o] = wv;
+    }
+    __syncthreads();
+    const int kmax = min(kFlKc, D - k0);
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int idx = threadIdx.x + 256 * a;
+      const int rr = idx / NOP, o = idx - rr * NOP;
+      const float* hr = h + (size_t)rr * D + k0;
+      float s = acc[a];
+      for (int kk = 0; kk < kmax; ++kk) s = fmaf(hr[kk], wT[kk * NOP + o], s);
+      acc[a] = s;
+    }
+  }
+  const int Wp = (int)(sqrtf((float)T) + 0.5f);
+  const int Himg = Wp * p;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const int idx = threadIdx.x + 256 * a;
+    const int rr = idx / NOP, o = idx - rr * NOP;
+    const int row = row0 + rr;
+    if (row < M && o < NO) {
+      float bv = bias[o];
+      if (round_bf16) bv = bf16_round(bv);
+      float r = acc[a] + bv;
+      if (round_bf16) r = bf16_round(r);
+      const int b = row / T, t = row - b * T;
+      const int hp = t / Wp, wp = t - hp * Wp;
+      const int c = o % Cout, pq = o / Cout;
+      const int pi = pq / p, qj = pq - pi * p;
+      out[(((size_t)b * Cout + c) * Himg + hp * p + pi) * Himg + wp * p + qj] = r;
+    }
+  }
+}
+
+}  // namespace ditb200
+
+using namespace ditb200;
+
+// ------------------------------------------------------------------ C entry points
+extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const float* scale,
+                                   int mod_stride, void* out, int out_dtype, float* stats, int B,
+                                   int T, int D, float eps, void* stream) {
+  DITB_REQUIRE(x && shift && scale && out, DITB200_EINVAL, "ln_modulate: null pointer");
+  DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0, DITB200_EINVAL,
+               "ln_modulate: need B,T > 0 and D %% 4 == 0 (D=%d)", D);
+  DITB_REQUIRE(mod_stride % 4 == 0, DITB200_EALIGN, "ln_modulate: mod_stride %% 4 != 0");
+  DITB_REQUIRE(aligned16(x) && aligned16(shift) && aligned16(scale) && aligned16(out),
+               DITB200_EALIGN, "ln_modulate: pointers must be 16-byte aligned");
+  DITB_REQUIRE(out_dtype == DITB200_F32 || out_dtype == DITB200_BF16, DITB200_EINVAL,
+               "ln_modulate: bad out_dtype %d", out_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * T;
+  const dim3 grid((M + 7) / 8), block(256);
+  const bool bf = out_dtype == DITB200_BF16;
+#define LN_CASE(NV)                                                                              \
+  case NV * 128:                                                                                 \
+    if (bf)                                                                                      \
+      ln_modulate_kernel<NV, true><<<grid, block, 0, st>>>(x, shift, scale, mod_stride, out,     \
+                                                           stats, M, T, eps);                    \
+    else                                                                                         \
+      ln_modulate_kernel<NV, false><<<grid, block, 0, st>>>(x, shift, scale, mod_stride, out,    \
+                                                            stats, M, T, eps);                   \
+    break;
+  switch (D) {
+    LN_CASE(3)
+    LN_CASE(6)
+    LN_CASE(8)
+    LN_CASE(9)
+    default:
+      if (bf)
+        ln_modulate_generic_kernel<true><<<grid, block, 0, st>>>(x, shift, scale, mod_stride, out,
+                                                                 stats, M, T, D, eps);
+      else
+        ln_modulate_generic_kernel<false><<<grid, block, 0, st>>>(x, shift, scale, mod_stride,
+                                                                  out, stats, M, T, D, eps);
+  }
+#undef LN_CASE
+  DITB_LAUNCH_CHECK("ln_modulate");
+  return 0;
+}
+
+extern "C" int ditb200_patch_embed(const float* x, const float* w, const float* bias,
+                                   const float* pos, float* out, int B, int C, int H, int W, int p,
+                                   int D, int round_bf16, void* stream) {
+  DITB_REQUIRE(x && w && bias && pos && out, DITB200_EINVAL, "patch_embed: null pointer");
+  DITB_REQUIRE(B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0 && D > 0, DITB200_EINVAL,
+               "patch_embed: bad shape B=%d C=%d H=%d W=%d p=%d D=%d", B, C, H, W, p, D);
+  const int K = C * p * p;
+  DITB_REQUIRE(K <= 1024, DITB200_EINVAL, "patch_embed: C*p*p = %d > 1024", K);
+  const int M = B * (H / p) * (W / p);
+  const size_t smem = (size_t)kPeTok * K * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(patch_embed_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_cuda(e, "patch_embed smem attr");
+  }
+  patch_embed_kernel<<<(M + kPeTok - 1) / kPeTok, 256, smem, (cudaStream_t)stream>>>(
+      x, w, bias, pos, out, B, C, H, W, p, D, round_bf16);
+  DITB_LAUNCH_CHECK("patch_embed");
+  return 0;
+}
+
+extern "C" int ditb200_timestep_embedding(const int64_t* t, float* out, int B, int dim,
+                                          float max_period, void* stream) {
+  DITB_REQUIRE(t && out && B > 0 && dim > 0 && max_period > 0.f, DITB200_EINVAL,
+               "timestep_embedding: bad argument");
+  const int n = B * dim;
+  // -math.log(max_period) is a Python double that torch rounds to f32 when it meets the f32 arange
+  const float neg_log = (float)(-log((double)max_period));
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, out, B, dim,
+                                                                                neg_log);
+  DITB_LAUNCH_CHECK("timestep_embedding");
+  return 0;
+}
+
+extern "C" int ditb200_label_embed(const int64_t* y, const float* table, const float* add,
+                                   float* out, int B, int D, int num_rows, void* stream) {
+  DITB_REQUIRE(y && table && out && B > 0 && D > 0 && num_rows > 0, DITB200_EINVAL,
+               "label_embed: bad argument");
+  const int n = B * D;
+  label_embed_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(y, table, add, out, B, D,
+                                                                         num_rows);
+  DITB_LAUNCH_CHECK("label_embed");
+  return 0;
+}
+
+extern "C" int ditb200_cast_bf16(const float* in, void* out, size_t n, void* stream) {
+  DITB_REQUIRE(in && out, DITB200_EINVAL, "cast_bf16: null pointer");
+  if (n == 0) return 0;
+  DITB_REQUIRE(aligned16(in) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0, DITB200_EALIGN,
+               "cast_bf16: misaligned pointer");
+  size_t blocks = (n / 4 + 255) / 256;
+  const size_t cap = (size_t)(num_sms() > 0 ? num_sms() : 148) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  DITB_LAUNCH_CHECK("cast_bf16");
+  return 0;
+}
+
+extern "C" int ditb200_final_layer(const float* x, const float* shift, const float* scale,
+                                   int mod_stride, const float* w, const float* bias, float* out,
+                                   int B, int T, int D, int p, int Cout, float eps, int round_bf16,
+                                   void* stream) {
+  DITB_REQUIRE(x && shift && scale && w && bias && out, DITB200_EINVAL, "final_layer: null pointer");
+  DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0 && p > 0 && Cout > 0, DITB200_EINVAL,
+               "final_layer: bad shape");
+  const int Wp = (int)(sqrt((double)T) + 0.5);
+  DITB_REQUIRE(Wp * Wp == T, DITB200_EINVAL, "final_layer: T=%d is not a square grid", T);
+  DITB_REQUIRE(mod_stride % 4 == 0 && aligned16(x) && aligned16(shift) && aligned16(scale),
+               DITB200_EALIGN, "final_layer: misaligned input");
+  const int NO = p * p * Cout;
+  const int now = (NO + 31) / 32;
+  DITB_REQUIRE(now <= 16, DITB200_EINVAL, "final_layer: p*p*Cout = %d > 512", NO);
+  const int M = B * T;
+  const dim3 grid((M + kFlRows - 1) / kFlRows), block(256);
+  cudaStream_t st = (cudaStream_t)stream;
+#define FL_LAUNCH(NOW)                                                                          \
+  {                                                                                             \
+    const size_t smem = ((size_t)kFlRows * D + (size_t)kFlKc * NOW * 32) * sizeof(float);       \
+    DITB_REQUIRE(smem <= 227 * 1024, DITB200_EINVAL, "final_layer: D=%d too large", D);         \
+    cudaError_t e = cudaFuncSetAttribute(final_layer_kernel<NOW>,                               \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return check_cuda(e, "final_layer smem attr");                        \
+    final_layer_kernel<NOW><<<grid, block, smem, st>>>(x, shift, scale, mod_stride, w, bias, out, \
+                                                       M, T, D, p, Cout, eps, round_bf16);      \
+  }
+  if (now == 1) FL_LAUNCH(1)
+  else if (now == 2) FL_LAUNCH(2)
+  else if (now <= 4) FL_LAUNCH(4)
+  else if (now <= 8) FL_LAUNCH(8)
+  else FL_LAUNCH(16)
+#undef FL_LAUNCH
+  DITB_LAUNCH_CHECK("final_layer");
+  return 0;
+}

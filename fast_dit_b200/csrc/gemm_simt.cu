@@ -1,0 +1,193 @@
+// gemm_simt.cu — f32 CUDA-core GEMM: the "fp32 check mode" engine and the small-M linears
+// (timestep MLP, adaLN modulation).  out = epilogue(act_in(A)[M,K] · W[N,K]ᵀ).
+//
+// 64x64 output tile per 256-thread CTA, 4x4 micro-tile per thread, K staged through shared
+// memory in slabs of 16 (stored k-major so the inner product reads are conflict-free
+// broadcasts).  Partial sums are flushed into the running accumulator every 32 k so the
+// rounding error grows like sqrt(K/32) instead of sqrt(K): the check mode has to sit within
+// 1e-5 of an fp32 reference through 28 blocks.
+#include "common.cuh"
+
+namespace ditb200 {
+
+constexpr int kTM = 64, kTN = 64, kTK = 16;
+
+struct SimtArgs {
+  const float* a;
+  int lda;
+  const void* w;  // [N, K] f32 or bf16
+  int w_bf16;
+  const float* bias;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ldo;
+  const float* add;  // small_linear: out += add[m, n]
+  int ldadd;
+  const float* resid;  // GATE_RESID
+  const float* gate;
+  int gate_stride, rows_per_gate;
+  int M, N, K;
+  int epilogue;
+  int silu_in;
+};
+
+__device__ __forceinline__ float load_w(const void* w, int w_bf16, size_t idx) {
+  if (w_bf16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(w)[idx]);
+  return reinterpret_cast<const float*>(w)[idx];
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
+  __shared__ float As[kTK][kTM + 4];
+  __shared__ float Ws[kTK][kTN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  float acc[4][4], part[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f, part[i][j] = 0.f;
+
+  // loader mapping: 256 threads load a 64 x 16 slab: row = tid / 4, k-group = (tid % 4) * 4
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  for (int k0 = 0; k0 < p.K; k0 += kTK) {
+    {
+      const int m = m0 + lrow;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + lk + j;
+        float v = 0.f;
+        if (m < p.M && k < p.K) {
+          v = p.a[(size_t)m * p.lda + k];
+          if (p.silu_in) v = silu_acc(v);
+        }
+        As[lk + j][lrow] = v;
+      }
+      const int n = n0 + lrow;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + lk + j;
+        float v = 0.f;
+        if (n < p.N && k < p.K) v = load_w(p.w, p.w_bf16, (size_t)n * p.K + k);
+        Ws[lk + j][lrow] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], wv[j], part[i][j]);
+    }
+    __syncthreads();
+    if (((k0 / kTK) & 1) == 1 || k0 + kTK >= p.K) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j], part[i][j] = 0.f;
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[n];
+      switch (p.epilogue) {
+        case DITB200_EPI_BIAS_GELU:
+          v = gelu_tanh_f(v);
+          break;
+        case DITB200_EPI_BIAS_SILU:
+          v = silu_acc(v);
+          break;
+        case DITB200_EPI_BIAS_GATE_RESID: {
+          const float g = p.gate[(size_t)(m / p.rows_per_gate) * p.gate_stride + n];
+          v = p.resid[(size_t)m * p.ldo + n] + g * v;
+        } break;
+        default:
+          break;
+      }
+      if (p.add) v += p.add[(size_t)m * p.ldadd + n];
+      if (p.out_bf16)
+        p.out_bf16[(size_t)m * p.ldo + n] = __float2bfloat16_rn(v);
+      else
+        p.out_f32[(size_t)m * p.ldo + n] = v;
+    }
+  }
+}
+
+int launch_gemm_simt(const SimtArgs& p, cudaStream_t st) {
+  dim3 grid((p.N + kTN - 1) / kTN, (p.M + kTM - 1) / kTM);
+  gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return check_cuda(e, "gemm_simt");
+  return 0;
+}
+
+// defined in gemm_tc.cu
+int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st);
+
+}  // namespace ditb200
+
+using namespace ditb200;
+
+extern "C" int ditb200_small_linear(const float* a, int lda, const void* w, int w_dtype,
+                                    const float* bias, const float* add, int ldadd, float* out,
+                                    int ldo, int M, int N, int K, int silu_in, int silu_out,
+                                    void* stream) {
+  DITB_REQUIRE(a && w && out, DITB200_EINVAL, "small_linear: null pointer");
+  DITB_REQUIRE(M > 0 && M <= 1024 && N > 0 && K > 0, DITB200_EINVAL,
+               "small_linear: bad shape M=%d N=%d K=%d (M <= 1024)", M, N, K);
+  DITB_REQUIRE(lda >= K && ldo >= N && (!add || ldadd >= N), DITB200_EINVAL,
+               "small_linear: bad leading dimension");
+  DITB_REQUIRE(w_dtype == DITB200_F32 || w_dtype == DITB200_BF16, DITB200_EINVAL,
+               "small_linear: bad w_dtype");
+  SimtArgs p{};
+  p.a = a, p.lda = lda, p.w = w, p.w_bf16 = (w_dtype == DITB200_BF16), p.bias = bias;
+  p.out_f32 = out, p.out_bf16 = nullptr, p.ldo = ldo, p.add = add, p.ldadd = ldadd;
+  p.M = M, p.N = N, p.K = K;
+  p.epilogue = silu_out ? DITB200_EPI_BIAS_SILU : DITB200_EPI_BIAS;
+  p.silu_in = silu_in;
+  return launch_gemm_simt(p, (cudaStream_t)stream);
+}
+
+extern "C" int ditb200_gemm(const ditb200_gemm_args* a, void* stream) {
+  DITB_REQUIRE(a != nullptr, DITB200_EINVAL, "gemm: null args");
+  DITB_REQUIRE(a->a && a->w && a->out, DITB200_EINVAL, "gemm: null tensor");
+  DITB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, DITB200_EINVAL, "gemm: bad shape %d %d %d", a->M,
+               a->N, a->K);
+  DITB_REQUIRE(a->epilogue >= 0 && a->epilogue <= 3, DITB200_EINVAL, "gemm: bad epilogue %d",
+               a->epilogue);
+  DITB_REQUIRE(a->out_dtype == DITB200_F32 || a->out_dtype == DITB200_BF16, DITB200_EINVAL,
+               "gemm: bad out_dtype");
+  if (a->epilogue == DITB200_EPI_BIAS_GATE_RESID) {
+    DITB_REQUIRE(a->resid && a->gate && a->rows_per_gate > 0 && a->gate_stride >= a->N,
+                 DITB200_EINVAL, "gemm: GATE_RESID needs resid, gate, rows_per_gate, gate_stride");
+    DITB_REQUIRE(a->out_dtype == DITB200_F32, DITB200_EINVAL,
+                 "gemm: GATE_RESID writes the f32 residual stream");
+  }
+  if (a->engine == DITB200_GEMM_TCGEN05) return launch_gemm_tcgen05(a, (cudaStream_t)stream);
+  DITB_REQUIRE(a->engine == DITB200_GEMM_FP32, DITB200_EINVAL, "gemm: bad engine %d", a->engine);
+  SimtArgs p{};
+  p.a = reinterpret_cast<const float*>(a->a), p.lda = a->K;
+  p.w = a->w, p.w_bf16 = 0, p.bias = a->bias;
+  if (a->out_dtype == DITB200_BF16)
+    p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out);
+  else
+    p.out_f32 = reinterpret_cast<float*>(a->out);
+  p.ldo = a->N;
+  p.resid = a->resid, p.gate = a->gate, p.gate_stride = a->gate_stride;
+  p.rows_per_gate = a->rows_per_gate;
+  p.M = a->M, p.N = a->N, p.K = a->K, p.epilogue = a->epilogue, p.silu_in = 0;
+  return launch_gemm_simt(p, (cudaStream_t)stream);
+}

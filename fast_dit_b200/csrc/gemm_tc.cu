@@ -1,0 +1,360 @@
+// gemm_tc.cu — the tensor-core GEMM of the DiT block: out = epilogue(A[M,K] · W[N,K]ᵀ), bf16
+// operands, f32 accumulation in tensor memory (TMEM), operands streamed by TMA.
+//
+// Structure (one persistent CTA per SM, or one CTA pair per two SMs with cta_group::2):
+//   warp 0      TMA producer: fills a ring of kStages {A 128x64, B (BN/kCG)x64} bf16 tiles,
+//               128-byte swizzled, signalling full[stage] with complete_tx bytes.
+//   warp 1      MMA issuer (one thread, leader CTA only): tcgen05.mma.kind::f16 128xBNx16 (or
+//               256xBNx16 across the pair) from shared-memory descriptors into one of two TMEM
+//               accumulator stages; tcgen05.commit releases smem slots / publishes accumulators.
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (thread = output row, 32 columns per
+//               load), apply bias / GELU-tanh / adaLN gate + residual, store to HBM, then hand
+//               the TMEM stage back.  Runs concurrently with the next tile's main loop.
+// Tiles are visited n-fastest so the CTAs running at the same time share A row-panels in L2
+// and the weight matrix stays L2-resident.
+#include "common.cuh"
+
+namespace ditb200 {
+
+constexpr int kBM = 128;       // rows per CTA tile = TMEM lanes
+constexpr int kBK = 64;        // 64 bf16 = one 128-byte swizzle row
+constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+struct EpiParams {
+  const float* bias;
+  void* out;
+  const float* resid;
+  const float* gate;
+  int gate_stride, rows_per_gate;
+  int epilogue, out_bf16;
+};
+
+template <int kCG, int BN>
+struct TcCfg {
+  static constexpr int kBRows = BN / kCG;  // B rows held by each CTA
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N");
+  static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+  static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle-128B tiles need 1024-B alignment");
+};
+
+template <int kCG, int BN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const EpiParams ep, const int M, const int N, const int K) {
+  using Cfg = TcCfg<kCG, BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms (same offset in both CTAs of a pair)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], kCG);  // producer arrive(s): own (+ peer's remote arrive)
+      mbar_init(&empty[s], 1);   // one tcgen05.commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4 * kCG);  // one arrive per epilogue warp of every CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kCG>(tmem_ptr, Cfg::kTmemCols);
+  tcgen05_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tile_m = kBM * kCG;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + kBK - 1) / kBK;
+  const int unit = blockIdx.x / kCG;       // CTA (pair) index
+  const int num_units = gridDim.x / kCG;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int row_a = m_blk * tile_m + (int)cta_rank * kBM;
+        const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          void* dst_a = smem_a + stage * Cfg::kABytes;
+          void* dst_b = smem_b + stage * Cfg::kBBytes;
+          if constexpr (kCG == 1) {
+            mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+            tma_load_2d(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
+            tma_load_2d(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
+          } else {
+            // both CTAs' bytes complete on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
+            tma_load_2d_pair(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
+            if (!leader) mbar_arrive_leader(&full[stage]);
+          }
+          if (++stage == kStages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================================= MMA issuer
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM * kCG, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = unit; tile < num_tiles; tile += num_units, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = umma_smem_desc_k128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = umma_smem_desc_k128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // +32 bytes (= 16 bf16) along K inside the swizzle atom: start address field += 2
+            umma_bf16<kCG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<kCG>(&empty[stage]);  // frees this smem slot (in both CTAs) when the MMAs retire
+          if (kb == k_blocks - 1) umma_commit<kCG>(&tmem_full[acc]);
+          if (++stage == kStages) stage = 0, phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ========================================================================= epilogue
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int row_in_tile = quarter * 32 + lane;
+    int iter = 0;
+    for (int tile = unit; tile < num_tiles; tile += num_units, ++iter) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int row = m_blk * tile_m + (int)cta_rank * kBM + row_in_tile;
+      const int col0 = n_blk * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const bool row_ok = row < M;
+      const float* gate_row = nullptr;
+      if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID && row_ok)
+        gate_row = ep.gate + (size_t)(row / ep.rows_per_gate) * ep.gate_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const int col = col0 + c * 32;
+        if (!row_ok || col >= N) continue;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col + j < N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
+              f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+            }
+          }
+        }
+        if (ep.epilogue == DITB200_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
+        } else if (ep.epilogue == DITB200_EPI_BIAS_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+        } else if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID) {
+          const float* rrow = ep.resid + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col + j < N) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate_row + col + j));
+              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+              f[j] = fmaf(g4.x, f[j], r4.x);
+              f[j + 1] = fmaf(g4.y, f[j + 1], r4.y);
+              f[j + 2] = fmaf(g4.z, f[j + 2], r4.z);
+              f[j + 3] = fmaf(g4.w, f[j + 3], r4.w);
+            }
+          }
+        }
+        if (ep.out_bf16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (col + j < N) {
+              uint4 pk;
+              pk.x = pack_bf16x2(f[j], f[j + 1]);
+              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+              *reinterpret_cast<uint4*>(orow + j) = pk;
+            }
+          }
+        } else {
+          float* orow = reinterpret_cast<float*>(ep.out) + (size_t)row * N + col;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col + j < N)
+              *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          }
+        }
+      }
+      // all tcgen05.ld of this stage are complete (wait::ld above): give the stage back
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc]);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc<kCG>(tmem_base, Cfg::kTmemCols);
+}
+
+// ----------------------------------------------------------------------------- host side
+static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("gemm: ditb200_init() has not been called");
+    return DITB200_ENOINIT;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};  // bytes, dim 1
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm: cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)",
+              (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows, box_cols);
+    return DITB200_EINVAL;
+  }
+  return 0;
+}
+
+template <int kCG, int BN>
+static int launch_cfg(const ditb200_gemm_args* a, cudaStream_t st) {
+  using Cfg = TcCfg<kCG, BN>;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d(&ta, a->a, (uint64_t)a->M, (uint64_t)a->K, kBM, kBK);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tb, a->w, (uint64_t)a->N, (uint64_t)a->K, Cfg::kBRows, kBK);
+  if (rc) return rc;
+  EpiParams ep;
+  ep.bias = a->bias, ep.out = a->out, ep.resid = a->resid, ep.gate = a->gate;
+  ep.gate_stride = a->gate_stride, ep.rows_per_gate = a->rows_per_gate;
+  ep.epilogue = a->epilogue, ep.out_bf16 = (a->out_dtype == DITB200_BF16);
+  static bool attr_set = false;  // per instantiation; benign race (idempotent)
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kCG, BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return check_cuda(e, "gemm_tc smem attribute");
+    attr_set = true;
+  }
+  const int tile_m = kBM * kCG;
+  const int tiles = ((a->M + tile_m - 1) / tile_m) * ((a->N + BN - 1) / BN);
+  int units = num_sms() / kCG;
+  if (units > tiles) units = tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(units * kCG));
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN>, ta, tb, ep, a->M, a->N, a->K);
+  if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
+  return 0;
+}
+
+// tile choice: minimise (waves x tile width); prefer CTA pairs (half the B traffic per SM)
+static void choose_tile(int M, int N, int sms, int* cg_out, int* bn_out) {
+  const int bns[3] = {256, 192, 128};
+  double best = 1e30;
+  int best_cg = 2, best_bn = 128;
+  for (int cg = 2; cg >= 1; --cg) {
+    for (int i = 0; i < 3; ++i) {
+      const int bn = bns[i];
+      const int tile_m = kBM * cg;
+      const long tiles = (long)((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
+      const long units = sms / cg;
+      const long waves = (tiles + units - 1) / units;
+      double cost = (double)waves * bn * (cg == 1 ? 1.03 : 1.0);
+      if (cost < best - 1e-9) best = cost, best_cg = cg, best_bn = bn;
+    }
+  }
+  *cg_out = best_cg, *bn_out = best_bn;
+}
+
+int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
+  DITB_REQUIRE(is_initialised(), DITB200_ENOINIT, "gemm: ditb200_init() has not been called");
+  DITB_REQUIRE(a->K % 8 == 0, DITB200_EINVAL, "gemm(tcgen05): K=%d must be a multiple of 8", a->K);
+  DITB_REQUIRE(a->N % 8 == 0, DITB200_EINVAL, "gemm(tcgen05): N=%d must be a multiple of 8", a->N);
+  DITB_REQUIRE(aligned16(a->a) && aligned16(a->w) && aligned16(a->out), DITB200_EALIGN,
+               "gemm(tcgen05): a, w, out must be 16-byte aligned");
+  DITB_REQUIRE(!a->bias || aligned16(a->bias), DITB200_EALIGN, "gemm(tcgen05): bias misaligned");
+  if (a->epilogue == DITB200_EPI_BIAS_GATE_RESID)
+    DITB_REQUIRE(aligned16(a->resid) && aligned16(a->gate) && a->gate_stride % 4 == 0,
+                 DITB200_EALIGN, "gemm(tcgen05): resid/gate misaligned");
+  int cg = a->cta_group, bn = a->tile_n;
+  if (cg == 0 || bn == 0) {
+    int acg, abn;
+    choose_tile(a->M, a->N, num_sms(), &acg, &abn);
+    if (cg == 0) cg = acg;
+    if (bn == 0) bn = abn;
+  }
+#define TC_CASE(CG, BN_)                   \
+  if (cg == CG && bn == BN_) return launch_cfg<CG, BN_>(a, st);
+  TC_CASE(1, 128)
+  TC_CASE(1, 192)
+  TC_CASE(1, 256)
+  TC_CASE(2, 128)
+  TC_CASE(2, 192)
+  TC_CASE(2, 256)
+#undef TC_CASE
+  set_error("gemm(tcgen05): unsupported tile cta_group=%d tile_n=%d", cg, bn);
+  return DITB200_EINVAL;
+}
+
+}  // namespace ditb200

@@ -1,0 +1,232 @@
+"""Thin torch-tensor wrappers over the libditb200 C-ABI.
+
+PyTorch is plumbing here: it owns device memory and the stream.  Every function
+takes CUDA tensors, passes raw pointers + the current stream to the library and
+returns the output tensor.  Nothing in this file computes on the host, and
+nothing falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise L.Ditb200Error("libditb200 ops need CUDA tensors (there is no CPU path)")
+    return L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_contig(*ts):
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise L.Ditb200Error("non-contiguous tensor passed to libditb200")
+
+
+# ------------------------------------------------------------------ embedders
+def patch_embed(x, w, bias, pos, p: int, round_bf16: bool = False):
+    """x[B,C,H,W] f32, w[D,C,p,p], bias[D], pos[T,D] (or [1,T,D]) -> [B*T, D] f32."""
+    lib = _lib_for(x)
+    _chk_contig(x, w, bias, pos)
+    B, Cc, H, W = x.shape
+    D = w.shape[0]
+    T = (H // p) * (W // p)
+    out = torch.empty((B * T, D), device=x.device, dtype=torch.float32)
+    L.check(lib.ditb200_patch_embed(_p(x), _p(w), _p(bias), _p(pos), _p(out), B, Cc, H, W, p, D,
+                                    int(round_bf16), _stream()), "patch_embed")
+    return out
+
+
+def timestep_embedding(t, dim: int, max_period: float = 10000.0):
+    lib = _lib_for(t)
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    t = t.contiguous()
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
+    L.check(lib.ditb200_timestep_embedding(_p(t), _p(out), t.shape[0], dim, float(max_period), _stream()),
+            "timestep_embedding")
+    return out
+
+
+def small_linear(a, w, bias=None, add=None, silu_in=False, silu_out=False, out=None):
+    """out[M,N] = act_out(act_in(a) @ w.T + bias) (+ add); a f32 [M,K]; w f32/bf16 [N,K]."""
+    lib = _lib_for(a)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.is_contiguous()
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    L.check(lib.ditb200_small_linear(_p(a), a.stride(0), _p(w), _DT[w.dtype], _p(bias), _p(add),
+                                     add.stride(0) if add is not None else 0, _p(out), out.stride(0),
+                                     M, N, K, int(silu_in), int(silu_out), _stream()), "small_linear")
+    return out
+
+
+def label_embed(y, table, add=None):
+    lib = _lib_for(table)
+    y = y.to(torch.int64).contiguous()
+    _chk_contig(table, add)
+    B, D = y.shape[0], table.shape[1]
+    out = torch.empty((B, D), device=table.device, dtype=torch.float32)
+    L.check(lib.ditb200_label_embed(_p(y), _p(table), _p(add), _p(out), B, D, table.shape[0], _stream()),
+            "label_embed")
+    return out
+
+
+# ------------------------------------------------------- LayerNorm + modulate
+def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None, out=None):
+    """x[B*T, D] f32; shift/scale: [B, D] views (unit inner stride, common row stride)."""
+    lib = _lib_for(x)
+    M, D = x.shape
+    B = M // T
+    assert x.is_contiguous() and shift.stride(1) == 1 and scale.stride(1) == 1
+    assert shift.stride(0) == scale.stride(0)
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=out_dtype)
+    L.check(lib.ditb200_ln_modulate(_p(x), _p(shift), _p(scale), shift.stride(0), _p(out), _DT[out.dtype],
+                                    _p(stats), B, T, D, float(eps), _stream()), "ln_modulate")
+    return out
+
+
+# ----------------------------------------------------------------------- GEMM
+def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
+         rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0):
+    """out = epilogue(a @ w.T).  a[M,K], w[N,K] both bf16 (tcgen05) or both f32 (check mode)."""
+    lib = _lib_for(a)
+    _chk_contig(a, w, bias, resid)
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.dtype == w.dtype
+    if engine is None:
+        engine = L.GEMM_TCGEN05 if a.dtype == torch.bfloat16 else L.GEMM_FP32
+    if epilogue == L.EPI_BIAS_GATE_RESID:
+        out_dtype = torch.float32
+        if out is None:
+            out = resid  # in place on the residual stream
+        assert gate is not None and gate.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
+    args = L.GemmArgs(_p(a), _p(w), _p(bias), _p(out), _p(resid), _p(gate),
+                      gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
+                      _DT[out.dtype], engine, tile_n, cta_group)
+    L.check(lib.ditb200_gemm(C.byref(args), _stream()), "gemm")
+    return out
+
+
+def cast_bf16(x, out=None):
+    lib = _lib_for(x)
+    _chk_contig(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(lib.ditb200_cast_bf16(_p(x), _p(out), x.numel(), _stream()), "cast_bf16")
+    return out
+
+
+# ------------------------------------------------------------------ attention
+def attention(qkv, B: int, T: int, H: int, hd: int, lse=None, out=None):
+    """qkv[B*T, 3*H*hd] -> out[B*T, H*hd], same dtype (bf16 or f32)."""
+    lib = _lib_for(qkv)
+    _chk_contig(qkv)
+    if out is None:
+        out = torch.empty((B * T, H * hd), device=qkv.device, dtype=qkv.dtype)
+    L.check(lib.ditb200_attention_fwd(_p(qkv), _p(out), _p(lse), _DT[qkv.dtype], B, T, H, hd, _stream()),
+            "attention_fwd")
+    return out
+
+
+# ---------------------------------------------------------------- final layer
+def final_layer(x, shift, scale, w, bias, T: int, p: int, c_out: int, eps: float = 1e-6,
+                round_bf16: bool = False):
+    """x[B*T, D] f32 -> [B, c_out, H, W] f32 (LN + modulate + linear + unpatchify)."""
+    lib = _lib_for(x)
+    _chk_contig(x, w, bias)
+    M, D = x.shape
+    B = M // T
+    hp = int(round(T ** 0.5))
+    out = torch.empty((B, c_out, hp * p, hp * p), device=x.device, dtype=torch.float32)
+    assert shift.stride(1) == 1 and shift.stride(0) == scale.stride(0)
+    L.check(lib.ditb200_final_layer(_p(x), _p(shift), _p(scale), shift.stride(0), _p(w), _p(bias), _p(out),
+                                    B, T, D, p, c_out, float(eps), int(round_bf16), _stream()),
+            "final_layer")
+    return out
+
+
+# ------------------------------------------------------------------ diffusion
+def cfg_combine(raw, n_cfg_ch: int, cfg_scale: float, out=None):
+    lib = _lib_for(raw)
+    _chk_contig(raw)
+    B, C2 = raw.shape[0], raw.shape[1]
+    HW = raw[0, 0].numel()
+    if out is None:
+        out = torch.empty_like(raw)
+    L.check(lib.ditb200_cfg_combine(_p(raw), _p(out), B // 2, C2, HW, n_cfg_ch, float(cfg_scale), _stream()),
+            "cfg_combine")
+    return out
+
+
+def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_denoised,
+                  cfg_half=0, n_cfg_ch=0, cfg_scale=1.0, want=("sample", "pred_xstart")):
+    """One fused ancestral step.  tables: dict of f32 device tensors (see diffusion/)."""
+    lib = _lib_for(x)
+    _chk_contig(model_out, x, noise, t)
+    B, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    outs = {k: torch.empty_like(x) for k in want}
+    if "sample" not in outs:
+        outs["sample"] = torch.empty_like(x)
+    args = L.StepArgs(
+        _p(model_out), _p(x), _p(noise), _p(t),
+        _p(tables.get("sqrt_recip_alphas_cumprod")), _p(tables.get("sqrt_recipm1_alphas_cumprod")),
+        _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
+        _p(tables["min_log"]), _p(tables.get("max_log")),
+        _p(outs["sample"]), _p(outs.get("pred_xstart")), _p(outs.get("mean")), _p(outs.get("log_variance")),
+        B, Cc, HW, int(tables["posterior_mean_coef1"].numel()),
+        mean_type, var_type, int(bool(clip_denoised)), int(cfg_half), int(n_cfg_ch), float(cfg_scale))
+    L.check(lib.ditb200_p_sample_step(C.byref(args), _stream()), "p_sample_step")
+    return outs
+
+
+def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
+    lib = _lib_for(x0)
+    _chk_contig(x0, noise, t)
+    out = torch.empty_like(x0)
+    B = x0.shape[0]
+    L.check(lib.ditb200_q_sample(_p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), B,
+                                 x0[0].numel(), int(sqrt_ac.numel()), _stream()), "q_sample")
+    return out
+
+
+def training_losses(model_out, x0, x_t, noise, t, tables, grad_scale: float = 0.0, want_grad: bool = False):
+    lib = _lib_for(x0)
+    _chk_contig(model_out, x0, x_t, noise, t)
+    B, Cc = x0.shape[0], x0.shape[1]
+    HW = x0[0, 0].numel()
+    dev = x0.device
+    mse = torch.empty(B, device=dev, dtype=torch.float32)
+    vb = torch.empty_like(mse)
+    loss = torch.empty_like(mse)
+    grad = torch.empty_like(model_out) if want_grad else None
+    args = L.LossArgs(
+        _p(model_out), _p(x0), _p(x_t), _p(noise), _p(t),
+        _p(tables["sqrt_recip_alphas_cumprod"]), _p(tables["sqrt_recipm1_alphas_cumprod"]),
+        _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
+        _p(tables["posterior_log_variance_clipped"]), _p(tables["log_betas"]),
+        _p(mse), _p(vb), _p(loss), _p(grad), float(grad_scale), B, Cc, HW,
+        int(tables["posterior_mean_coef1"].numel()))
+    L.check(lib.ditb200_training_losses(C.byref(args), _stream()), "training_losses")
+    return {"mse": mse, "vb": vb, "loss": loss, "grad_model_out": grad}

@@ -1,0 +1,245 @@
+/*
+ * ditb200.h — C-ABI of libditb200.so, the B200 (sm_100a) denoiser hot path.
+ *
+ * The reference (alexandor91/fast-DiT) has no FFI: its boundary is Python duck
+ * typing over torch ops.  Each entry point below replaces the torch/timm
+ * library call(s) named in its comment (file:line relative to the reference
+ * tree).  The Python mirror of the reference interface lives in
+ * fast_dit_b200/{models.py,diffusion/}; INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller (PyTorch's caching
+ *     allocator).  The library allocates nothing after ditb200_init() and keeps
+ *     no pointer past the call.
+ *   - Every entry point is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*), re-entrant, and safe to call from PyTorch's autograd thread.
+ *   - Return value: 0 = OK, negative = argument/shape error (DITB200_E*),
+ *     positive = cudaError_t.  ditb200_last_error() returns the message of the
+ *     last failure on the calling thread.
+ *   - dtype codes: DITB200_F32 = 0, DITB200_BF16 = 1.
+ *   - "tokens" are rows of the [M = B*T, D] activation matrix, row-major.
+ */
+#ifndef DITB200_H_
+#define DITB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DITB200_ABI_VERSION 1
+
+#define DITB200_F32 0
+#define DITB200_BF16 1
+
+#define DITB200_EINVAL (-1)   /* bad argument / unsupported shape */
+#define DITB200_ENOINIT (-2)  /* ditb200_init() not called for this device */
+#define DITB200_EALIGN (-3)   /* pointer or stride not aligned as required */
+
+/* GEMM epilogues (what is fused after acc = A·Wᵀ) */
+#define DITB200_EPI_BIAS 0            /* out = acc + bias                              */
+#define DITB200_EPI_BIAS_GELU 1       /* out = gelu_tanh(acc + bias)                   */
+#define DITB200_EPI_BIAS_GATE_RESID 2 /* out_f32 = resid + gate[row/T] * (acc + bias)  */
+#define DITB200_EPI_BIAS_SILU 3       /* out = silu(acc + bias)                        */
+
+/* GEMM engines */
+#define DITB200_GEMM_TCGEN05 0 /* bf16 operands, tcgen05.mma + TMEM accumulators, TMA-fed */
+#define DITB200_GEMM_FP32 1    /* fp32 operands, CUDA-core FFMA (the "fp32 check mode")    */
+
+/* diffusion model-output conventions (gaussian_diffusion.py:25-45) */
+#define DITB200_MEAN_EPSILON 0
+#define DITB200_MEAN_START_X 1
+#define DITB200_VAR_LEARNED_RANGE 0
+#define DITB200_VAR_LEARNED 1
+#define DITB200_VAR_FIXED 2 /* FIXED_SMALL / FIXED_LARGE: log-variance read from a table */
+
+int ditb200_abi_version(void);
+/* One-off per process+device: resolves the driver's tensor-map encoder, reads
+ * the SM count, raises dynamic shared-memory limits.  Idempotent. */
+int ditb200_init(int device);
+const char* ditb200_last_error(void);
+int ditb200_sm_count(void);
+
+/* ---------------------------------------------------------------- embedders */
+
+/* PatchEmbed + pos_embed: Conv2d(C→D, k=s=p) ≡ per-patch GEMM, flatten NCHW →
+ * [B,T,D], add the frozen sin-cos table.
+ * Replaces timm PatchEmbed.forward + `+ self.pos_embed`
+ * (train_options/models_original.py:169,240).
+ * x[B,C,H,W] f32; w[D, C*p*p] f32 (conv weight flattened); bias[D]; pos[T,D];
+ * out[B*T, D] f32.  round_bf16 != 0 rounds operands and the conv result to
+ * bf16 first (what torch.autocast does to conv2d). */
+int ditb200_patch_embed(const float* x, const float* w, const float* bias, const float* pos,
+                        float* out, int B, int C, int H, int W, int p, int D, int round_bf16,
+                        void* stream);
+
+/* Sinusoidal timestep features, cos half first.
+ * Replaces TimestepEmbedder.timestep_embedding (models_original.py:40-59).
+ * t[B] int64 → out[B, dim] f32. */
+int ditb200_timestep_embedding(const int64_t* t, float* out, int B, int dim, float max_period,
+                               void* stream);
+
+/* Small-M linear: out[m, n] = act_out( sum_k act_in(a[m,k]) * w[n,k] + bias[n] ) (+ add[m,n]).
+ * Replaces nn.Linear / nn.SiLU in TimestepEmbedder.mlp (models_original.py:33-37),
+ * DiTBlock.adaLN_modulation (:113-116) and FinalLayer.adaLN_modulation (:134-137).
+ * a[M,K] f32 (row stride lda); w[N,K] f32 or bf16 (w_dtype); bias[N] f32 or NULL;
+ * add[M,N] f32 or NULL (row stride ldadd); out[M,N] f32 (row stride ldo).
+ * silu_in / silu_out: apply SiLU to the input / to the result.  M <= 1024. */
+int ditb200_small_linear(const float* a, int lda, const void* w, int w_dtype, const float* bias,
+                         const float* add, int ldadd, float* out, int ldo, int M, int N, int K,
+                         int silu_in, int silu_out, void* stream);
+
+/* Label embedding gather: out[b,:] = table[y[b],:] (+ add[b,:]).
+ * Replaces LabelEmbedder.forward's nn.Embedding and `c = t + y`
+ * (models_original.py:93,243).  Label dropout (token_drop, :79-87) stays on
+ * the host because it consumes torch's RNG stream. */
+int ditb200_label_embed(const int64_t* y, const float* table, const float* add, float* out, int B,
+                        int D, int num_rows, void* stream);
+
+/* ------------------------------------------------------- LayerNorm + modulate */
+
+/* out[b,t,:] = LN(x[b,t,:]) * (1 + scale[b,:]) + shift[b,:], LN without affine,
+ * biased variance, statistics in f32.
+ * Replaces nn.LayerNorm(elementwise_affine=False, eps=1e-6) + modulate()
+ * (models_original.py:19-20,107,109,120-121).
+ * x[B*T, D] f32; shift/scale point at [B, D] slices with row stride mod_stride
+ * (floats); out[B*T, D] of out_dtype.  If stats != NULL, writes mean and rstd
+ * per row to stats[2*row], stats[2*row+1] (saved for backward). */
+int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, int mod_stride,
+                        void* out, int out_dtype, float* stats, int B, int T, int D, float eps,
+                        void* stream);
+
+/* ----------------------------------------------------------------- GEMMs */
+
+typedef struct ditb200_gemm_args {
+  const void* a;      /* [M, K] row-major, bf16 (TCGEN05) or f32 (FP32)                  */
+  const void* w;      /* [N, K] row-major (nn.Linear layout), same dtype as a            */
+  const float* bias;  /* [N] f32 or NULL                                                 */
+  void* out;          /* [M, N] row-major; dtype out_dtype (f32 required for GATE_RESID) */
+  const float* resid; /* GATE_RESID: [M, N] f32 (may alias out)                          */
+  const float* gate;  /* GATE_RESID: gate[(row / rows_per_gate) * gate_stride + col]     */
+  int gate_stride;
+  int rows_per_gate; /* T: tokens per image */
+  int M, N, K;
+  int epilogue;  /* DITB200_EPI_*  */
+  int out_dtype; /* DITB200_F32 / DITB200_BF16 */
+  int engine;    /* DITB200_GEMM_* */
+  int tile_n;    /* TCGEN05 only: output-tile width 128/192/256, 0 = choose from the shape */
+  int cta_group; /* TCGEN05 only: 1 = one CTA per tile, 2 = CTA pair (256-row tile), 0 = choose */
+} ditb200_gemm_args;
+
+/* out = epilogue(a · wᵀ).  Replaces, per DiTBlock: timm Attention.qkv (EPI_BIAS),
+ * Attention.proj + `x + gate_msa * (.)` (EPI_BIAS_GATE_RESID; models_original.py:120),
+ * Mlp.fc1 + GELU(tanh) (EPI_BIAS_GELU; :110-112), Mlp.fc2 + `x + gate_mlp * (.)` (:121).
+ * TCGEN05 engine: K % 64 == 0, N % 16 == 0, pointers 16-byte aligned. */
+int ditb200_gemm(const ditb200_gemm_args* args, void* stream);
+
+/* f32 → bf16 cast of a contiguous array (weight shadows). n elements. */
+int ditb200_cast_bf16(const float* in, void* out, size_t n, void* stream);
+
+/* ------------------------------------------------------------- attention */
+
+/* Fused multi-head attention forward, softmax(q kᵀ / sqrt(hd)) v, non-causal.
+ * Replaces timm Attention.forward's reshape/permute + F.scaled_dot_product_attention
+ * + transpose/reshape (see performance/A100/train_original.out:36-37 for the layout).
+ * qkv[B*T, 3*H*hd] token-major as the qkv Linear writes it (cols: Q heads | K heads |
+ * V heads); out[B*T, H*hd] token-major (what proj consumes).  dtype of both =
+ * dtype.  lse (optional, f32 [B,H,T]) receives log-sum-exp rows for backward. */
+int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
+                          int hd, void* stream);
+
+/* ----------------------------------------------------------- final layer */
+
+/* FinalLayer after its adaLN: LN + modulate + Linear(D → p*p*Cout) + unpatchify
+ * into NCHW.  Replaces FinalLayer.forward's norm/modulate/linear
+ * (models_original.py:138-142) and DiT.unpatchify (:218-231).
+ * x[B*T, D] f32; shift/scale [B,D] slices (row stride mod_stride); w[p*p*Cout, D]
+ * f32; bias[p*p*Cout]; out[B, Cout, Hp*p, Wp*p] f32 with T = Hp*Wp, Hp == Wp.
+ * round_bf16 != 0 rounds the modulated activations and weights to bf16 first. */
+int ditb200_final_layer(const float* x, const float* shift, const float* scale, int mod_stride,
+                        const float* w, const float* bias, float* out, int B, int T, int D, int p,
+                        int Cout, float eps, int round_bf16, void* stream);
+
+/* ------------------------------------------------------------- diffusion */
+
+/* Classifier-free-guidance combine on the model output.
+ * Replaces DiT.forward_with_cfg's slicing/cat arithmetic (models_original.py:258-266):
+ * for the first n_cfg_ch channels, both halves := u + s*(c - u); other channels
+ * pass through.  raw[2n, C2, HW] f32 → out[2n, C2, HW] f32 (may alias raw). */
+int ditb200_cfg_combine(const float* raw, float* out, int n_half, int C2, int HW, int n_cfg_ch,
+                        float cfg_scale, void* stream);
+
+typedef struct ditb200_step_args {
+  const float* model_out; /* [B, C2, HW] f32; C2 = 2C if learned variance else C */
+  const float* x;         /* [B, C, HW] f32: x_t */
+  const float* noise;     /* [B, C, HW] f32 or NULL (then sample = mean) */
+  const int64_t* t;       /* [B] int64 indices into the tables */
+  /* f32 tables of length num_timesteps (fp64 tables of GaussianDiffusion.__init__,
+   * gaussian_diffusion.py:153-201, rounded once to f32 — _extract_into_tensor casts
+   * after the gather, :870, which is the same value) */
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* min_log;  /* LEARNED_RANGE: posterior_log_variance_clipped; FIXED: the log-variance table */
+  const float* max_log;  /* LEARNED_RANGE: log(betas) */
+  float* sample;         /* [B, C, HW] out */
+  float* pred_xstart;    /* [B, C, HW] out or NULL */
+  float* mean;           /* optional out */
+  float* log_variance;   /* optional out */
+  int B, C, HW;
+  int num_timesteps;
+  int mean_type;     /* DITB200_MEAN_* */
+  int var_type;      /* DITB200_VAR_*  */
+  int clip_denoised; /* clamp pred_xstart to [-1, 1] */
+  int cfg_half;      /* > 0: model_out is the raw two-half CFG batch (n = cfg_half); the
+                        combine of ditb200_cfg_combine is applied on the fly */
+  int n_cfg_ch;
+  float cfg_scale;
+} ditb200_step_args;
+
+/* One ancestral sampling step x_t → x_{t-1}, fully fused.
+ * Replaces GaussianDiffusion.p_mean_variance + _predict_xstart_from_eps +
+ * q_posterior_mean_variance + the update in p_sample
+ * (diffusion/gaussian_diffusion.py:285-293, 320-323, 334-339, 238-241, 410-416)
+ * and, with cfg_half > 0, forward_with_cfg's combine (models_original.py:258-266). */
+int ditb200_p_sample_step(const ditb200_step_args* args, void* stream);
+
+/* q_sample: x_t = sqrt_ac[t]*x0 + sqrt_1mac[t]*noise (gaussian_diffusion.py:215-230). */
+int ditb200_q_sample(const float* x0, const float* noise, const int64_t* t,
+                     const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
+                     float* x_t, int B, int CHW, int num_timesteps, void* stream);
+
+typedef struct ditb200_loss_args {
+  const float* model_out; /* [B, 2C, HW] f32 */
+  const float* x0;        /* [B, C, HW] */
+  const float* x_t;       /* [B, C, HW] */
+  const float* noise;     /* [B, C, HW] */
+  const int64_t* t;
+  const float* sqrt_recip_alphas_cumprod;
+  const float* sqrt_recipm1_alphas_cumprod;
+  const float* posterior_mean_coef1;
+  const float* posterior_mean_coef2;
+  const float* posterior_log_variance_clipped;
+  const float* log_betas;
+  float* mse;             /* [B] out */
+  float* vb;              /* [B] out */
+  float* loss;            /* [B] out: mse + vb */
+  float* grad_model_out;  /* [B, 2C, HW] out or NULL: d(sum_b loss[b] * grad_scale)/d model_out */
+  float grad_scale;       /* e.g. 1/B for loss.mean() */
+  int B, C, HW, num_timesteps;
+} ditb200_loss_args;
+
+/* training_losses for MSE + LEARNED_RANGE + EPSILON (what create_diffusion("")
+ * builds): mse, vb (KL or decoder NLL at t == 0, in bits), loss, and the gradient
+ * wrt the model output, one kernel with warp-shuffle row reductions.
+ * Replaces gaussian_diffusion.py:747-781, 682-713 and diffusion_utils.py:10-36,62-88. */
+int ditb200_training_losses(const ditb200_loss_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DITB200_H_ */
