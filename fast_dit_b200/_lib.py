@@ -18,6 +18,7 @@ EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RESID, EPI_BIAS_SILU = 0, 1, 2, 3
 GEMM_TCGEN05, GEMM_FP32 = 0, 1
 MEAN_EPSILON, MEAN_START_X = 0, 1
 VAR_LEARNED_RANGE, VAR_LEARNED, VAR_FIXED = 0, 1, 2
+SAMPLER_ANCESTRAL, SAMPLER_DDIM = 0, 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -37,7 +38,8 @@ class StepArgs(C.Structure):
         ("sqrt_recip_alphas_cumprod", _vp), ("sqrt_recipm1_alphas_cumprod", _vp),
         ("posterior_mean_coef1", _vp), ("posterior_mean_coef2", _vp),
         ("min_log", _vp), ("max_log", _vp),
-        ("sample", _vp), ("pred_xstart", _vp), ("mean", _vp), ("log_variance", _vp),
+        ("sample", _vp), ("pred_xstart", _vp), ("mean", _vp), ("log_variance", _vp), ("variance", _vp),
+        ("alphas_cumprod", _vp), ("alphas_cumprod_prev", _vp), ("eta", _f), ("sampler", _i),
         ("B", _i), ("C", _i), ("HW", _i), ("num_timesteps", _i),
         ("mean_type", _i), ("var_type", _i), ("clip_denoised", _i),
         ("cfg_half", _i), ("n_cfg_ch", _i), ("cfg_scale", _f),
@@ -51,7 +53,7 @@ class LossArgs(C.Structure):
         ("posterior_mean_coef1", _vp), ("posterior_mean_coef2", _vp),
         ("posterior_log_variance_clipped", _vp), ("log_betas", _vp),
         ("mse", _vp), ("vb", _vp), ("loss", _vp), ("grad_model_out", _vp),
-        ("grad_scale", _f),
+        ("w_mse", _vp), ("w_vb", _vp), ("vb_scale", _f),
         ("B", _i), ("C", _i), ("HW", _i), ("num_timesteps", _i),
     ]
 
@@ -69,6 +71,7 @@ SIGNATURES = {
     "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
     "ditb200_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "ditb200_cast_bf16": (_i, [_vp, _vp, _sz, _vp]),
+    "ditb200_silu_cast": (_i, [_vp, _vp, _i, _sz, _vp]),
     "ditb200_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ditb200_final_layer": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ditb200_cfg_combine": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),

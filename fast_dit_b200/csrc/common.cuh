@@ -119,8 +119,9 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 }
 // arrive on the barrier at the same smem offset in CTA 0 (the leader) of the cluster
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, 0))
-               : "memory");
+  // default semantics on purpose: an explicit .release.cluster costs a MEMBAR.ALL.CTA + ERRBAR
+  // (waits for every outstanding global store of the thread) in front of each arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, 0)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;

@@ -55,6 +55,7 @@ __global__ void cfg_combine_kernel(const float* __restrict__ raw, float* __restr
 // fetched once per thread (L1/L2-resident, a few hundred bytes in total).
 struct StepCoef {
   float srac, srm1, c1, c2, min_log, max_log, nonzero;
+  float ab, ab_prev;  // DDIM
 };
 
 __device__ __forceinline__ StepCoef load_coef(const ditb200_step_args& a, int b) {
@@ -69,6 +70,11 @@ __device__ __forceinline__ StepCoef load_coef(const ditb200_step_args& a, int b)
   k.min_log = a.min_log[t];
   k.max_log = (a.var_type == DITB200_VAR_LEARNED_RANGE) ? a.max_log[t] : 0.f;
   k.nonzero = (t != 0) ? 1.f : 0.f;
+  k.ab = k.ab_prev = 1.f;
+  if (a.sampler == DITB200_SAMPLER_DDIM) {
+    k.ab = a.alphas_cumprod[t];
+    k.ab_prev = a.alphas_cumprod_prev[t];
+  }
   return k;
 }
 
@@ -92,6 +98,16 @@ __device__ __forceinline__ void step_math(const ditb200_step_args& a, const Step
   if (a.clip_denoised) pred = fminf(fmaxf(pred, -1.0f), 1.0f);
   // posterior mean (:238-241)
   mean = fadd(fmul(k.c1, pred), fmul(k.c2, x));
+  if (a.sampler == DITB200_SAMPLER_DDIM) {
+    // ddim_sample (:541-560): eps re-derived from pred_xstart, Eq. 12 of the DDIM paper
+    const float eps = __fdiv_rn(fsub(fmul(k.srac, x), pred), k.srm1);
+    const float sigma = fmul(fmul(a.eta, sqrtf(__fdiv_rn(fsub(1.0f, k.ab_prev), fsub(1.0f, k.ab)))),
+                             sqrtf(fsub(1.0f, __fdiv_rn(k.ab, k.ab_prev))));
+    const float mean_pred = fadd(fmul(pred, sqrtf(k.ab_prev)),
+                                 fmul(sqrtf(fsub(fsub(1.0f, k.ab_prev), fmul(sigma, sigma))), eps));
+    sample = fadd(mean_pred, fmul(fmul(k.nonzero, sigma), noise));
+    return;
+  }
   // ancestral update (:410-416): mean + nonzero_mask * exp(0.5 * logvar) * noise
   sample = fadd(mean, fmul(fmul(k.nonzero, expf(fmul(0.5f, logvar))), noise));
 }
@@ -144,6 +160,8 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(const ditb200_step_a
     if (a.mean) *reinterpret_cast<float4*>(a.mean + off) = make_float4(m[0], m[1], m[2], m[3]);
     if (a.log_variance)
       *reinterpret_cast<float4*>(a.log_variance + off) = make_float4(lv[0], lv[1], lv[2], lv[3]);
+    if (a.variance)
+      *reinterpret_cast<float4*>(a.variance + off) = make_float4(expf(lv[0]), expf(lv[1]), expf(lv[2]), expf(lv[3]));
   }
 }
 
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(256) p_sample_step_scalar_kernel(const ditb200
     if (a.pred_xstart) a.pred_xstart[idx] = p;
     if (a.mean) a.mean[idx] = m;
     if (a.log_variance) a.log_variance[idx] = lv;
+    if (a.variance) a.variance[idx] = expf(lv);
   }
 }
 
@@ -273,8 +292,8 @@ __global__ void __launch_bounds__(256) training_losses_kernel(const ditb200_loss
     }
     s_vb += term;
     if (g_eps) {
-      g_eps[i] = a.grad_scale * 2.0f * (eps - n) * inv_n;
-      g_v[i] = a.grad_scale * inv_n * inv_ln2 * dterm_dlv2 * 0.5f * (max_log - min_log);
+      g_eps[i] = a.w_mse[b] * 2.0f * (eps - n) * inv_n;
+      g_v[i] = a.w_vb[b] * a.vb_scale * inv_n * inv_ln2 * dterm_dlv2 * 0.5f * (max_log - min_log);
     }
   }
   s_mse = warp_sum(s_mse);
@@ -291,7 +310,7 @@ __global__ void __launch_bounds__(256) training_losses_kernel(const ditb200_loss
     m = warp_sum(m);
     v = warp_sum(v);
     if (lane == 0) {
-      const float mse = m * inv_n, vb = v * inv_n * inv_ln2;
+      const float mse = m * inv_n, vb = v * inv_n * inv_ln2 * a.vb_scale;
       a.mse[b] = mse;
       a.vb[b] = vb;
       a.loss[b] = mse + vb;
@@ -337,6 +356,10 @@ extern "C" int ditb200_p_sample_step(const ditb200_step_args* a, void* stream) {
                "p_sample_step: LEARNED_RANGE needs max_log");
   DITB_REQUIRE(a->var_type >= 0 && a->var_type <= 2 && a->mean_type >= 0 && a->mean_type <= 1,
                DITB200_EINVAL, "p_sample_step: bad mean/var type");
+  DITB_REQUIRE(a->sampler == DITB200_SAMPLER_ANCESTRAL ||
+                   (a->sampler == DITB200_SAMPLER_DDIM && a->alphas_cumprod && a->alphas_cumprod_prev &&
+                    a->sqrt_recip_alphas_cumprod && a->sqrt_recipm1_alphas_cumprod),
+               DITB200_EINVAL, "p_sample_step: DDIM needs the alphas_cumprod(+prev) and recip tables");
   DITB_REQUIRE(a->cfg_half == 0 || a->B == 2 * a->cfg_half, DITB200_EINVAL,
                "p_sample_step: cfg_half=%d but B=%d", a->cfg_half, a->B);
   ditb200_step_args k = *a;
@@ -347,7 +370,8 @@ extern "C" int ditb200_p_sample_step(const ditb200_step_args* a, void* stream) {
                    aligned16(a->sample) && (!a->noise || aligned16(a->noise)) &&
                    (!a->pred_xstart || aligned16(a->pred_xstart)) &&
                    (!a->mean || aligned16(a->mean)) &&
-                   (!a->log_variance || aligned16(a->log_variance));
+                   (!a->log_variance || aligned16(a->log_variance)) &&
+                   (!a->variance || aligned16(a->variance));
   const size_t total = (size_t)a->B * a->C * a->HW;
   if (vec)
     p_sample_step_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(k);
@@ -378,6 +402,8 @@ extern "C" int ditb200_training_losses(const ditb200_loss_args* a, void* stream)
                DITB200_EINVAL, "training_losses: null table");
   DITB_REQUIRE(a->B > 0 && a->C > 0 && a->HW > 0 && a->num_timesteps > 0, DITB200_EINVAL,
                "training_losses: bad shape");
+  DITB_REQUIRE(!a->grad_model_out || (a->w_mse && a->w_vb), DITB200_EINVAL,
+               "training_losses: grad_model_out needs w_mse and w_vb");
   training_losses_kernel<<<a->B, 256, 0, (cudaStream_t)stream>>>(*a);
   DITB_LAUNCH_CHECK("training_losses");
   return 0;

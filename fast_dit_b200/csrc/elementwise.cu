@@ -218,6 +218,19 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
   }
 }
 
+// SiLU then cast: the A operand of the batched adaLN GEMM (nn.SiLU of MO:114 on c[N, D])
+template <bool kOutBf16>
+__global__ void silu_cast_kernel(const float* __restrict__ in, void* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = silu_acc(in[i]);
+    if constexpr (kOutBf16)
+      reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(out)[i] = v;
+  }
+}
+
 // ================================================================= final layer
 // CTA = kFlRows token rows.  Phase 1: one warp normalises + modulates two rows into shared
 // memory.  Phase 2: a [kFlRows x NO] mini-GEMM against the (transposed, k-chunked) weight,
@@ -431,6 +444,22 @@ extern "C" int ditb200_cast_bf16(const float* in, void* out, size_t n, void* str
   cast_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       in, reinterpret_cast<__nv_bfloat16*>(out), n);
   DITB_LAUNCH_CHECK("cast_bf16");
+  return 0;
+}
+
+extern "C" int ditb200_silu_cast(const float* in, void* out, int out_dtype, size_t n, void* stream) {
+  DITB_REQUIRE(in && out, DITB200_EINVAL, "silu_cast: null pointer");
+  DITB_REQUIRE(out_dtype == DITB200_F32 || out_dtype == DITB200_BF16, DITB200_EINVAL,
+               "silu_cast: bad out_dtype");
+  if (n == 0) return 0;
+  size_t blocks = (n + 255) / 256;
+  const size_t cap = (size_t)(num_sms() > 0 ? num_sms() : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (out_dtype == DITB200_BF16)
+    silu_cast_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  else
+    silu_cast_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  DITB_LAUNCH_CHECK("silu_cast");
   return 0;
 }
 

@@ -71,7 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], kCG);  // producer arrive(s): own (+ peer's remote arrive)
+      mbar_init(&full[s], 1);    // one arrive.expect_tx (leader CTA) covering every CTA's bytes
       mbar_init(&empty[s], 1);   // one tcgen05.commit per phase
     }
     for (int s = 0; s < 2; ++s) {
@@ -112,11 +112,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
             tma_load_2d(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
           } else {
-            // both CTAs' bytes complete on the leader's barrier
+            // Both CTAs' bytes complete on the leader's barrier, which only the leader arms.  The
+            // peer may run ahead of the arming: its empty[stage] wait guarantees the leader's
+            // barrier is already in the matching phase, and a transiently negative tx-count
+            // cannot complete the phase while the leader's arrival is still pending.
             if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
             tma_load_2d_pair(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
             tma_load_2d_pair(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
-            if (!leader) mbar_arrive_leader(&full[stage]);
           }
           if (++stage == kStages) stage = 0, phase ^= 1u;
         }

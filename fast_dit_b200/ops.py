@@ -31,6 +31,51 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+LAUNCHES = 0          # kernels launched through this module since import (bench.py reads deltas)
+_PROFILE = None       # list of (name, start_event, end_event, meta) while profile() is active
+
+
+class profile:
+    """Context manager: brackets every kernel launch with CUDA events on the launching stream.
+
+        with ops.profile() as p: model(x, t, y)
+        p.summary() -> {kernel name: (launches, total ms)}
+    """
+
+    def __enter__(self):
+        global _PROFILE
+        self.records = []
+        _PROFILE = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+        torch.cuda.synchronize()
+        return False
+
+    def summary(self):
+        out = {}
+        for name, e0, e1, meta in self.records:
+            n, ms, flops = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), flops + (meta or 0.0))
+        return out
+
+
+def _call(name, fn, *args, meta=None):
+    """Invoke one C-ABI entry point (= one kernel launch) and check its return code."""
+    global LAUNCHES
+    LAUNCHES += 1
+    if _PROFILE is None:
+        L.check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(fn(*args), name)
+    e1.record()
+    _PROFILE.append((name, e0, e1, meta))
+
+
 def _chk_contig(*ts):
     for t in ts:
         if t is not None and not t.is_contiguous():
@@ -46,8 +91,8 @@ def patch_embed(x, w, bias, pos, p: int, round_bf16: bool = False):
     D = w.shape[0]
     T = (H // p) * (W // p)
     out = torch.empty((B * T, D), device=x.device, dtype=torch.float32)
-    L.check(lib.ditb200_patch_embed(_p(x), _p(w), _p(bias), _p(pos), _p(out), B, Cc, H, W, p, D,
-                                    int(round_bf16), _stream()), "patch_embed")
+    _call("patch_embed", lib.ditb200_patch_embed, _p(x), _p(w), _p(bias), _p(pos), _p(out), B, Cc, H, W, p, D,
+                                    int(round_bf16), _stream())
     return out
 
 
@@ -57,8 +102,7 @@ def timestep_embedding(t, dim: int, max_period: float = 10000.0):
         t = t.to(torch.int64)
     t = t.contiguous()
     out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
-    L.check(lib.ditb200_timestep_embedding(_p(t), _p(out), t.shape[0], dim, float(max_period), _stream()),
-            "timestep_embedding")
+    _call("timestep_embedding", lib.ditb200_timestep_embedding, _p(t), _p(out), t.shape[0], dim, float(max_period), _stream())
     return out
 
 
@@ -71,9 +115,9 @@ def small_linear(a, w, bias=None, add=None, silu_in=False, silu_out=False, out=N
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
     assert out.stride(1) == 1
-    L.check(lib.ditb200_small_linear(_p(a), a.stride(0), _p(w), _DT[w.dtype], _p(bias), _p(add),
+    _call("small_linear", lib.ditb200_small_linear, _p(a), a.stride(0), _p(w), _DT[w.dtype], _p(bias), _p(add),
                                      add.stride(0) if add is not None else 0, _p(out), out.stride(0),
-                                     M, N, K, int(silu_in), int(silu_out), _stream()), "small_linear")
+                                     M, N, K, int(silu_in), int(silu_out), _stream())
     return out
 
 
@@ -83,8 +127,7 @@ def label_embed(y, table, add=None):
     _chk_contig(table, add)
     B, D = y.shape[0], table.shape[1]
     out = torch.empty((B, D), device=table.device, dtype=torch.float32)
-    L.check(lib.ditb200_label_embed(_p(y), _p(table), _p(add), _p(out), B, D, table.shape[0], _stream()),
-            "label_embed")
+    _call("label_embed", lib.ditb200_label_embed, _p(y), _p(table), _p(add), _p(out), B, D, table.shape[0], _stream())
     return out
 
 
@@ -98,8 +141,8 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
     assert shift.stride(0) == scale.stride(0)
     if out is None:
         out = torch.empty((M, D), device=x.device, dtype=out_dtype)
-    L.check(lib.ditb200_ln_modulate(_p(x), _p(shift), _p(scale), shift.stride(0), _p(out), _DT[out.dtype],
-                                    _p(stats), B, T, D, float(eps), _stream()), "ln_modulate")
+    _call("ln_modulate", lib.ditb200_ln_modulate, _p(x), _p(shift), _p(scale), shift.stride(0), _p(out), _DT[out.dtype],
+                                    _p(stats), B, T, D, float(eps), _stream())
     return out
 
 
@@ -124,7 +167,8 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
     args = L.GemmArgs(_p(a), _p(w), _p(bias), _p(out), _p(resid), _p(gate),
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
                       _DT[out.dtype], engine, tile_n, cta_group)
-    L.check(lib.ditb200_gemm(C.byref(args), _stream()), "gemm")
+    _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
+          meta=2.0 * M * N * K)
     return out
 
 
@@ -133,7 +177,15 @@ def cast_bf16(x, out=None):
     _chk_contig(x)
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    L.check(lib.ditb200_cast_bf16(_p(x), _p(out), x.numel(), _stream()), "cast_bf16")
+    _call("cast_bf16", lib.ditb200_cast_bf16, _p(x), _p(out), x.numel(), _stream())
+    return out
+
+
+def silu_cast(x, out_dtype=torch.bfloat16):
+    lib = _lib_for(x)
+    _chk_contig(x)
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    _call("silu_cast", lib.ditb200_silu_cast, _p(x), _p(out), _DT[out_dtype], x.numel(), _stream())
     return out
 
 
@@ -144,8 +196,8 @@ def attention(qkv, B: int, T: int, H: int, hd: int, lse=None, out=None):
     _chk_contig(qkv)
     if out is None:
         out = torch.empty((B * T, H * hd), device=qkv.device, dtype=qkv.dtype)
-    L.check(lib.ditb200_attention_fwd(_p(qkv), _p(out), _p(lse), _DT[qkv.dtype], B, T, H, hd, _stream()),
-            "attention_fwd")
+    _call("attention_fwd", lib.ditb200_attention_fwd, _p(qkv), _p(out), _p(lse), _DT[qkv.dtype], B, T, H, hd, _stream(),
+          meta=4.0 * B * H * T * T * hd)
     return out
 
 
@@ -160,9 +212,8 @@ def final_layer(x, shift, scale, w, bias, T: int, p: int, c_out: int, eps: float
     hp = int(round(T ** 0.5))
     out = torch.empty((B, c_out, hp * p, hp * p), device=x.device, dtype=torch.float32)
     assert shift.stride(1) == 1 and shift.stride(0) == scale.stride(0)
-    L.check(lib.ditb200_final_layer(_p(x), _p(shift), _p(scale), shift.stride(0), _p(w), _p(bias), _p(out),
-                                    B, T, D, p, c_out, float(eps), int(round_bf16), _stream()),
-            "final_layer")
+    _call("final_layer", lib.ditb200_final_layer, _p(x), _p(shift), _p(scale), shift.stride(0), _p(w), _p(bias), _p(out),
+                                    B, T, D, p, c_out, float(eps), int(round_bf16), _stream())
     return out
 
 
@@ -174,13 +225,13 @@ def cfg_combine(raw, n_cfg_ch: int, cfg_scale: float, out=None):
     HW = raw[0, 0].numel()
     if out is None:
         out = torch.empty_like(raw)
-    L.check(lib.ditb200_cfg_combine(_p(raw), _p(out), B // 2, C2, HW, n_cfg_ch, float(cfg_scale), _stream()),
-            "cfg_combine")
+    _call("cfg_combine", lib.ditb200_cfg_combine, _p(raw), _p(out), B // 2, C2, HW, n_cfg_ch, float(cfg_scale), _stream())
     return out
 
 
 def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_denoised,
-                  cfg_half=0, n_cfg_ch=0, cfg_scale=1.0, want=("sample", "pred_xstart")):
+                  cfg_half=0, n_cfg_ch=0, cfg_scale=1.0, want=("sample", "pred_xstart"),
+                  sampler=L.SAMPLER_ANCESTRAL, eta=0.0):
     """One fused ancestral step.  tables: dict of f32 device tensors (see diffusion/)."""
     lib = _lib_for(x)
     _chk_contig(model_out, x, noise, t)
@@ -195,9 +246,11 @@ def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_d
         _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
         _p(tables["min_log"]), _p(tables.get("max_log")),
         _p(outs["sample"]), _p(outs.get("pred_xstart")), _p(outs.get("mean")), _p(outs.get("log_variance")),
+        _p(outs.get("variance")), _p(tables.get("alphas_cumprod")), _p(tables.get("alphas_cumprod_prev")),
+        float(eta), int(sampler),
         B, Cc, HW, int(tables["posterior_mean_coef1"].numel()),
         mean_type, var_type, int(bool(clip_denoised)), int(cfg_half), int(n_cfg_ch), float(cfg_scale))
-    L.check(lib.ditb200_p_sample_step(C.byref(args), _stream()), "p_sample_step")
+    _call("p_sample_step", lib.ditb200_p_sample_step, C.byref(args), _stream())
     return outs
 
 
@@ -206,27 +259,29 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     _chk_contig(x0, noise, t)
     out = torch.empty_like(x0)
     B = x0.shape[0]
-    L.check(lib.ditb200_q_sample(_p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), B,
-                                 x0[0].numel(), int(sqrt_ac.numel()), _stream()), "q_sample")
+    _call("q_sample", lib.ditb200_q_sample, _p(x0), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), B,
+                                 x0[0].numel(), int(sqrt_ac.numel()), _stream())
     return out
 
 
-def training_losses(model_out, x0, x_t, noise, t, tables, grad_scale: float = 0.0, want_grad: bool = False):
+def training_losses(model_out, x0, x_t, noise, t, tables, vb_scale: float = 1.0, w_mse=None, w_vb=None):
+    """mse / vb / loss per sample; with w_mse and w_vb ([B] upstream gradients) also the gradient
+    with respect to model_out."""
     lib = _lib_for(x0)
-    _chk_contig(model_out, x0, x_t, noise, t)
+    _chk_contig(model_out, x0, x_t, noise, t, w_mse, w_vb)
     B, Cc = x0.shape[0], x0.shape[1]
     HW = x0[0, 0].numel()
     dev = x0.device
     mse = torch.empty(B, device=dev, dtype=torch.float32)
     vb = torch.empty_like(mse)
     loss = torch.empty_like(mse)
-    grad = torch.empty_like(model_out) if want_grad else None
+    grad = torch.empty_like(model_out) if w_mse is not None else None
     args = L.LossArgs(
         _p(model_out), _p(x0), _p(x_t), _p(noise), _p(t),
         _p(tables["sqrt_recip_alphas_cumprod"]), _p(tables["sqrt_recipm1_alphas_cumprod"]),
         _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
         _p(tables["posterior_log_variance_clipped"]), _p(tables["log_betas"]),
-        _p(mse), _p(vb), _p(loss), _p(grad), float(grad_scale), B, Cc, HW,
+        _p(mse), _p(vb), _p(loss), _p(grad), _p(w_mse), _p(w_vb), float(vb_scale), B, Cc, HW,
         int(tables["posterior_mean_coef1"].numel()))
-    L.check(lib.ditb200_training_losses(C.byref(args), _stream()), "training_losses")
+    _call("training_losses", lib.ditb200_training_losses, C.byref(args), _stream())
     return {"mse": mse, "vb": vb, "loss": loss, "grad_model_out": grad}

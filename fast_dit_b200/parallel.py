@@ -1,0 +1,98 @@
+"""Data-parallel execution of the denoiser path on one 8xB200 box.
+
+Sampling shards by batch exactly as /root/reference/sample_ddp.py does (cited SD:line): one
+process per GPU, weights replicated, every rank draws its own latents/labels from the seed
+`global_seed * world_size + rank` (SD:57-58) and runs an independent p_sample_loop; images never
+interact, so there is NO collective inside the loop — only the barriers around it (SD:92,141).
+Sample k of iteration i on rank r gets the global index `i * per_iter_total + k * world + r`
+(SD:136).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    world_size: int
+    rank: int
+    per_proc_batch: int
+    num_samples: int
+
+    @property
+    def global_batch(self) -> int:  # SD:97
+        return self.per_proc_batch * self.world_size
+
+    @property
+    def total_samples(self) -> int:
+        """num_samples rounded up to a multiple of the global batch (SD:99)."""
+        return int(math.ceil(self.num_samples / self.global_batch) * self.global_batch)
+
+    @property
+    def samples_this_rank(self) -> int:  # SD:103
+        return self.total_samples // self.world_size
+
+    @property
+    def iterations(self) -> int:  # SD:105
+        return self.samples_this_rank // self.per_proc_batch
+
+    def seed(self, global_seed: int) -> int:  # SD:57
+        return global_seed * self.world_size + self.rank
+
+    def global_index(self, iteration: int, k: int) -> int:
+        """Index of the k-th image this rank produces in `iteration` (SD:134-138)."""
+        return iteration * self.global_batch + k * self.world_size + self.rank
+
+    def all_indices(self) -> list[int]:
+        return [self.global_index(i, k) for i in range(self.iterations) for k in range(self.per_proc_batch)]
+
+
+def make_cfg_batch(n: int, latent_size: int, num_classes: int, device, in_channels: int = 4, generator=None):
+    """One iteration's inputs (SD:110-118): z ~ N(0,1), y ~ U{0..num_classes-1}, then the
+    classifier-free-guidance doubling z = [z; z], y = [y; null]."""
+    z = torch.randn(n, in_channels, latent_size, latent_size, device=device, generator=generator)
+    y = torch.randint(0, num_classes, (n,), device=device, generator=generator)
+    z = torch.cat([z, z], 0)
+    y = torch.cat([y, torch.full((n,), num_classes, device=device, dtype=y.dtype)], 0)
+    return z, y
+
+
+@torch.no_grad()
+def sample_shard(model, diffusion, plan: ShardPlan, *, latent_size: int, num_classes: int = 1000,
+                 cfg_scale: float = 4.0, global_seed: int = 0, device="cuda", on_batch=None):
+    """Run this rank's share of a sample_ddp job.  Returns [(global indices, latents [n,C,H,W])]
+    per iteration, or streams them to on_batch(indices, latents)."""
+    torch.manual_seed(plan.seed(global_seed))
+    n = plan.per_proc_batch
+    results = []
+    for it in range(plan.iterations):
+        z, y = make_cfg_batch(n, latent_size, num_classes, device, model.in_channels)
+        samples = diffusion.p_sample_loop(model.forward_with_cfg, z.shape, z, clip_denoised=False,
+                                          model_kwargs=dict(y=y, cfg_scale=cfg_scale), progress=False, device=device)
+        samples, _ = samples.chunk(2, dim=0)  # drop the null-class half (SD:129)
+        idx = [plan.global_index(it, k) for k in range(n)]
+        if on_batch is not None:
+            on_batch(idx, samples)
+        else:
+            results.append((idx, samples))
+    return results
+
+
+def init_from_env(backend: str = "nccl"):
+    """torchrun plumbing: returns (rank, local_rank, world_size); initialises torch.distributed
+    when WORLD_SIZE > 1."""
+    import os
+
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local, world

@@ -56,6 +56,10 @@ extern "C" {
 #define DITB200_VAR_LEARNED 1
 #define DITB200_VAR_FIXED 2 /* FIXED_SMALL / FIXED_LARGE: log-variance read from a table */
 
+/* update rule of ditb200_p_sample_step */
+#define DITB200_SAMPLER_ANCESTRAL 0 /* p_sample  (gaussian_diffusion.py:376-417) */
+#define DITB200_SAMPLER_DDIM 1      /* ddim_sample (gaussian_diffusion.py:513-560) */
+
 int ditb200_abi_version(void);
 /* One-off per process+device: resolves the driver's tensor-map encoder, reads
  * the SM count, raises dynamic shared-memory limits.  Idempotent. */
@@ -140,6 +144,10 @@ int ditb200_gemm(const ditb200_gemm_args* args, void* stream);
 /* f32 → bf16 cast of a contiguous array (weight shadows). n elements. */
 int ditb200_cast_bf16(const float* in, void* out, size_t n, void* stream);
 
+/* out[i] = silu(in[i]) cast to out_dtype: the nn.SiLU in front of every adaLN_modulation
+ * Linear (models_original.py:114,135), producing the A operand of the batched adaLN GEMM. */
+int ditb200_silu_cast(const float* in, void* out, int out_dtype, size_t n, void* stream);
+
 /* ------------------------------------------------------------- attention */
 
 /* Fused multi-head attention forward, softmax(q kᵀ / sqrt(hd)) v, non-causal.
@@ -190,6 +198,12 @@ typedef struct ditb200_step_args {
   float* pred_xstart;    /* [B, C, HW] out or NULL */
   float* mean;           /* optional out */
   float* log_variance;   /* optional out */
+  float* variance;       /* optional out: exp(log_variance) */
+  /* DDIM only (sampler == DITB200_SAMPLER_DDIM): alphas_cumprod / alphas_cumprod_prev tables */
+  const float* alphas_cumprod;
+  const float* alphas_cumprod_prev;
+  float eta;
+  int sampler;           /* DITB200_SAMPLER_* */
   int B, C, HW;
   int num_timesteps;
   int mean_type;     /* DITB200_MEAN_* */
@@ -201,10 +215,11 @@ typedef struct ditb200_step_args {
   float cfg_scale;
 } ditb200_step_args;
 
-/* One ancestral sampling step x_t → x_{t-1}, fully fused.
+/* One sampling step x_t → x_{t-1}, fully fused.
  * Replaces GaussianDiffusion.p_mean_variance + _predict_xstart_from_eps +
  * q_posterior_mean_variance + the update in p_sample
- * (diffusion/gaussian_diffusion.py:285-293, 320-323, 334-339, 238-241, 410-416)
+ * (diffusion/gaussian_diffusion.py:285-293, 320-323, 334-339, 238-241, 410-416),
+ * or the DDIM update of ddim_sample (:541-560) when sampler == DITB200_SAMPLER_DDIM,
  * and, with cfg_half > 0, forward_with_cfg's combine (models_original.py:258-266). */
 int ditb200_p_sample_step(const ditb200_step_args* args, void* stream);
 
@@ -228,8 +243,10 @@ typedef struct ditb200_loss_args {
   float* mse;             /* [B] out */
   float* vb;              /* [B] out */
   float* loss;            /* [B] out: mse + vb */
-  float* grad_model_out;  /* [B, 2C, HW] out or NULL: d(sum_b loss[b] * grad_scale)/d model_out */
-  float grad_scale;       /* e.g. 1/B for loss.mean() */
+  float* grad_model_out;  /* [B, 2C, HW] out or NULL: d(sum_b w_mse[b]*mse[b] + w_vb[b]*vb[b]) / d model_out */
+  const float* w_mse;     /* [B] upstream gradients of mse (+loss); required with grad_model_out */
+  const float* w_vb;      /* [B] upstream gradients of vb (+loss) */
+  float vb_scale;         /* 1, or num_timesteps/1000 for RESCALED_MSE (gaussian_diffusion.py:766-769) */
   int B, C, HW, num_timesteps;
 } ditb200_loss_args;
 
