@@ -39,7 +39,7 @@ class StepArgs(C.Structure):
         ("posterior_mean_coef1", _vp), ("posterior_mean_coef2", _vp),
         ("min_log", _vp), ("max_log", _vp),
         ("sample", _vp), ("pred_xstart", _vp), ("mean", _vp), ("log_variance", _vp), ("variance", _vp),
-        ("alphas_cumprod", _vp), ("alphas_cumprod_prev", _vp), ("eta", _f), ("sampler", _i),
+        ("var_table", _vp), ("alphas_cumprod", _vp), ("alphas_cumprod_prev", _vp), ("eta", _f), ("sampler", _i),
         ("B", _i), ("C", _i), ("HW", _i), ("num_timesteps", _i),
         ("mean_type", _i), ("var_type", _i), ("clip_denoised", _i),
         ("cfg_half", _i), ("n_cfg_ch", _i), ("cfg_scale", _f),

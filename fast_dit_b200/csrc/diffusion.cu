@@ -160,8 +160,16 @@ __global__ void __launch_bounds__(256) p_sample_step_kernel(const ditb200_step_a
     if (a.mean) *reinterpret_cast<float4*>(a.mean + off) = make_float4(m[0], m[1], m[2], m[3]);
     if (a.log_variance)
       *reinterpret_cast<float4*>(a.log_variance + off) = make_float4(lv[0], lv[1], lv[2], lv[3]);
-    if (a.variance)
-      *reinterpret_cast<float4*>(a.variance + off) = make_float4(expf(lv[0]), expf(lv[1]), expf(lv[2]), expf(lv[3]));
+    if (a.variance) {
+      if (a.var_table != nullptr) {
+        long long tt = a.t[b];
+        tt = tt < 0 ? 0 : (tt >= a.num_timesteps ? a.num_timesteps - 1 : tt);
+        const float vt = a.var_table[tt];
+        *reinterpret_cast<float4*>(a.variance + off) = make_float4(vt, vt, vt, vt);
+      } else {
+        *reinterpret_cast<float4*>(a.variance + off) = make_float4(expf(lv[0]), expf(lv[1]), expf(lv[2]), expf(lv[3]));
+      }
+    }
   }
 }
 
@@ -188,7 +196,11 @@ __global__ void __launch_bounds__(256) p_sample_step_scalar_kernel(const ditb200
     if (a.pred_xstart) a.pred_xstart[idx] = p;
     if (a.mean) a.mean[idx] = m;
     if (a.log_variance) a.log_variance[idx] = lv;
-    if (a.variance) a.variance[idx] = expf(lv);
+    if (a.variance) {
+      long long tt = a.t[b];
+      tt = tt < 0 ? 0 : (tt >= a.num_timesteps ? a.num_timesteps - 1 : tt);
+      a.variance[idx] = (a.var_table != nullptr) ? a.var_table[tt] : expf(lv);
+    }
   }
 }
 

@@ -147,11 +147,27 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(
 #pragma unroll
     for (int tt = 0; tt < kPeTok; ++tt) acc[tt] = 0.f;
     const float* wr = w + (size_t)d * K;
-    for (int k = 0; k < K; ++k) {
-      float wv = __ldg(wr + k);
-      if (round_bf16) wv = bf16_round(wv);
+    if ((K & 3) == 0) {
+      // four k per step: one 128-bit weight load and one 128-bit (broadcast) patch load per token
+      for (int k = 0; k < K; k += 4) {
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+        if (round_bf16) w4 = make_float4(bf16_round(w4.x), bf16_round(w4.y), bf16_round(w4.z), bf16_round(w4.w));
 #pragma unroll
-      for (int tt = 0; tt < kPeTok; ++tt) acc[tt] = fmaf(wv, patch[tt * K + k], acc[tt]);
+        for (int tt = 0; tt < kPeTok; ++tt) {
+          const float4 p4 = *reinterpret_cast<const float4*>(&patch[tt * K + k]);
+          acc[tt] = fmaf(w4.x, p4.x, acc[tt]);
+          acc[tt] = fmaf(w4.y, p4.y, acc[tt]);
+          acc[tt] = fmaf(w4.z, p4.z, acc[tt]);
+          acc[tt] = fmaf(w4.w, p4.w, acc[tt]);
+        }
+      }
+    } else {
+      for (int k = 0; k < K; ++k) {
+        float wv = __ldg(wr + k);
+        if (round_bf16) wv = bf16_round(wv);
+#pragma unroll
+        for (int tt = 0; tt < kPeTok; ++tt) acc[tt] = fmaf(wv, patch[tt * K + k], acc[tt]);
+      }
     }
     float bv = bias[d];
     if (round_bf16) bv = bf16_round(bv);
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(256) final_layer_kernel(
     float* __restrict__ out, int M, int T, int D, int p, int Cout, float eps, int round_bf16) {
   extern __shared__ float smem[];
   float* h = smem;                         // [kFlRows][D]
-  float* wT = smem + (size_t)kFlRows * D;  // [kFlKc][NOW*32]
+  float* wT = smem + (size_t)kFlRows * D;  // [NOW*32][kFlKc + 4]
   constexpr int NOP = NOW * 32;
   const int NO = p * p * Cout;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,48 +310,67 @@ __global__ void __launch_bounds__(256) final_layer_kernel(
     }
   }
   // ---- phase 2
-  constexpr int NACC = kFlRows * NOP / 256;  // outputs per thread
-  float acc[NACC];
+  // thread -> OT output columns x RT rows.  All accumulators of a thread reuse its 128-bit weight
+  // reads (OT per 4 k) and the broadcast 128-bit h reads (RT per 4 k): OT*RT*4 FMAs per OT+RT loads.
+  constexpr int NOPT = NOP < 256 ? NOP : 256;  // output columns covered by one pass of the CTA
+  constexpr int OT = NOP / NOPT;
+  constexpr int rstep = 256 / NOPT;
+  constexpr int RT = kFlRows / rstep;
+  constexpr int WLD = kFlKc + 4;  // padded row stride of the weight slab: conflict-free float4 reads
+  float acc[OT][RT];
 #pragma unroll
-  for (int a = 0; a < NACC; ++a) acc[a] = 0.f;
+  for (int j = 0; j < OT; ++j)
+#pragma unroll
+    for (int a = 0; a < RT; ++a) acc[j][a] = 0.f;
+  const int o0 = threadIdx.x % NOPT;
+  const int rr0 = threadIdx.x / NOPT;
   for (int k0 = 0; k0 < D; k0 += kFlKc) {
-    __syncthreads();  // h complete (first pass) / previous chunk consumed
+    __syncthreads();  // h complete (first pass) / previous slab consumed
     for (int idx = threadIdx.x; idx < NOP * kFlKc; idx += 256) {
-      const int o = idx / kFlKc, kk = idx - o * kFlKc;
+      const int oo = idx / kFlKc, kk = idx - oo * kFlKc;
       float wv = 0.f;
-      if (o < NO && k0 + kk < D) wv = __ldg(w + (size_t)o * D + k0 + kk);
+      if (oo < NO && k0 + kk < D) wv = __ldg(w + (size_t)oo * D + k0 + kk);
       if (round_bf16) wv = bf16_round(wv);
-      wT[kk * NOP + o] = wv;
+      wT[oo * WLD + kk] = wv;
     }
     __syncthreads();
-    const int kmax = min(kFlKc, D - k0);
+    const int kmax = min(kFlKc, D - k0);  // D % 4 == 0
+    for (int kk = 0; kk < kmax; kk += 4) {
+      float4 w4[OT];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) {
-      const int idx = threadIdx.x + 256 * a;
-      const int rr = idx / NOP, o = idx - rr * NOP;
-      const float* hr = h + (size_t)rr * D + k0;
-      float s = acc[a];
-      for (int kk = 0; kk < kmax; ++kk) s = fmaf(hr[kk], wT[kk * NOP + o], s);
-      acc[a] = s;
+      for (int j = 0; j < OT; ++j) w4[j] = *reinterpret_cast<const float4*>(&wT[(o0 + j * NOPT) * WLD + kk]);
+#pragma unroll
+      for (int a = 0; a < RT; ++a) {
+        const float4 h4 = *reinterpret_cast<const float4*>(h + (size_t)(rr0 + a * rstep) * D + k0 + kk);
+#pragma unroll
+        for (int j = 0; j < OT; ++j) {
+          acc[j][a] = fmaf(h4.x, w4[j].x, acc[j][a]);
+          acc[j][a] = fmaf(h4.y, w4[j].y, acc[j][a]);
+          acc[j][a] = fmaf(h4.z, w4[j].z, acc[j][a]);
+          acc[j][a] = fmaf(h4.w, w4[j].w, acc[j][a]);
+        }
+      }
     }
   }
   const int Wp = (int)(sqrtf((float)T) + 0.5f);
   const int Himg = Wp * p;
 #pragma unroll
-  for (int a = 0; a < NACC; ++a) {
-    const int idx = threadIdx.x + 256 * a;
-    const int rr = idx / NOP, o = idx - rr * NOP;
-    const int row = row0 + rr;
-    if (row < M && o < NO) {
-      float bv = bias[o];
-      if (round_bf16) bv = bf16_round(bv);
-      float r = acc[a] + bv;
-      if (round_bf16) r = bf16_round(r);
-      const int b = row / T, t = row - b * T;
-      const int hp = t / Wp, wp = t - hp * Wp;
-      const int c = o % Cout, pq = o / Cout;
-      const int pi = pq / p, qj = pq - pi * p;
-      out[(((size_t)b * Cout + c) * Himg + hp * p + pi) * Himg + wp * p + qj] = r;
+  for (int j = 0; j < OT; ++j) {
+    const int o = o0 + j * NOPT;
+#pragma unroll
+    for (int a = 0; a < RT; ++a) {
+      const int row = row0 + rr0 + a * rstep;
+      if (row < M && o < NO) {
+        float bv = bias[o];
+        if (round_bf16) bv = bf16_round(bv);
+        float r = acc[j][a] + bv;
+        if (round_bf16) r = bf16_round(r);
+        const int b = row / T, t = row - b * T;
+        const int hp = t / Wp, wp = t - hp * Wp;
+        const int c = o % Cout, pq = o / Cout;
+        const int pi = pq / p, qj = pq - pi * p;
+        out[(((size_t)b * Cout + c) * Himg + hp * p + pi) * Himg + wp * p + qj] = r;
+      }
     }
   }
 }
@@ -482,7 +517,7 @@ extern "C" int ditb200_final_layer(const float* x, const float* shift, const flo
   cudaStream_t st = (cudaStream_t)stream;
 #define FL_LAUNCH(NOW)                                                                          \
   {                                                                                             \
-    const size_t smem = ((size_t)kFlRows * D + (size_t)kFlKc * NOW * 32) * sizeof(float);       \
+    const size_t smem = ((size_t)kFlRows * D + (size_t)(kFlKc + 4) * NOW * 32) * sizeof(float);       \
     DITB_REQUIRE(smem <= 227 * 1024, DITB200_EINVAL, "final_layer: D=%d too large", D);         \
     cudaError_t e = cudaFuncSetAttribute(final_layer_kernel<NOW>,                               \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -94,17 +94,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int unit = blockIdx.x / kCG;       // CTA (pair) index
   const int num_units = gridDim.x / kCG;
 
+  // Producer and MMA roles run warp-uniform loops (every lane waits on the barriers) and elect one
+  // lane only around the asynchronous issues.  Keeping the control flow uniform lets the compiler
+  // hold descriptors / barrier addresses in uniform registers; a divergent `if (lane == 0)` loop
+  // costs a vector->uniform register move in front of every UTCHMMA and made the issue thread the
+  // bottleneck (profiles/r01_gemm_notes.md).
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = unit; tile < num_tiles; tile += num_units) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-        const int row_a = m_blk * tile_m + (int)cta_rank * kBM;
-        const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = unit; tile < num_tiles; tile += num_units) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int row_a = m_blk * tile_m + (int)cta_rank * kBM;
+      const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           void* dst_a = smem_a + stage * Cfg::kABytes;
           void* dst_b = smem_b + stage * Cfg::kBBytes;
           if constexpr (kCG == 1) {
@@ -120,14 +125,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             tma_load_2d_pair(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
             tma_load_2d_pair(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
           }
-          if (++stage == kStages) stage = 0, phase ^= 1u;
         }
+        __syncwarp();
+        if (++stage == kStages) stage = 0, phase ^= 1u;
       }
     }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM * kCG, BN);
+      // descriptor = {lo: start address >> 4, hi: SBO 1024 B | version 1 | SWIZZLE_128B}
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4;
+      const uint32_t b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -140,16 +150,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
-          const uint64_t da = umma_smem_desc_k128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = umma_smem_desc_k128(smem_u32(smem_b + stage * Cfg::kBBytes));
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * (Cfg::kABytes >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)stage * (Cfg::kBBytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // +32 bytes (= 16 bf16) along K inside the swizzle atom: start address field += 2
-            umma_bf16<kCG>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // +32 bytes (= 16 bf16) along K inside the swizzle atom: start-address field += 2
+              const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + 2 * k);
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + 2 * k);
+              umma_bf16<kCG>(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit<kCG>(&empty[stage]);  // frees this smem slot (in both CTAs) when the MMAs retire
+            if (kb == k_blocks - 1) umma_commit<kCG>(&tmem_full[acc]);
           }
-          umma_commit<kCG>(&empty[stage]);  // frees this smem slot (in both CTAs) when the MMAs retire
-          if (kb == k_blocks - 1) umma_commit<kCG>(&tmem_full[acc]);
+          __syncwarp();
           if (++stage == kStages) stage = 0, phase ^= 1u;
         }
       }
@@ -310,23 +324,14 @@ static int launch_cfg(const ditb200_gemm_args* a, cudaStream_t st) {
   return 0;
 }
 
-// tile choice: minimise (waves x tile width); prefer CTA pairs (half the B traffic per SM)
+// Tile choice, from measurements on B200 (profiles/r01_gemm_notes.md): the widest tile wins for every
+// DiT shape because the per-k-block issue/barrier cost is amortised over twice the MMA work, and the
+// CTA pair halves each SM's B traffic.  Narrow tiles only when N itself is narrow; single CTAs when M
+// fits one 128-row tile (adaLN, M = batch).
 static void choose_tile(int M, int N, int sms, int* cg_out, int* bn_out) {
-  const int bns[3] = {256, 192, 128};
-  double best = 1e30;
-  int best_cg = 2, best_bn = 128;
-  for (int cg = 2; cg >= 1; --cg) {
-    for (int i = 0; i < 3; ++i) {
-      const int bn = bns[i];
-      const int tile_m = kBM * cg;
-      const long tiles = (long)((M + tile_m - 1) / tile_m) * ((N + bn - 1) / bn);
-      const long units = sms / cg;
-      const long waves = (tiles + units - 1) / units;
-      double cost = (double)waves * bn * (cg == 1 ? 1.03 : 1.0);
-      if (cost < best - 1e-9) best = cost, best_cg = cg, best_bn = bn;
-    }
-  }
-  *cg_out = best_cg, *bn_out = best_bn;
+  (void)sms;
+  *cg_out = (M > kBM) ? 2 : 1;
+  *bn_out = (N > 192) ? 256 : (N > 128) ? 192 : 128;
 }
 
 int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {

@@ -169,8 +169,11 @@ class GaussianDiffusion:
         if vt == ModelVarType.LEARNED_RANGE:
             tab["min_log"], tab["max_log"] = tab["posterior_log_variance_clipped"], tab["log_betas"]
         elif vt == ModelVarType.FIXED_LARGE:  # GD:298-301
-            tab["min_log"] = up(np.log(np.append(self.posterior_variance[1], self.betas[1:])))
-        else:  # FIXED_SMALL (GD:302-305); LEARNED ignores it
+            v = np.append(self.posterior_variance[1], self.betas[1:])
+            tab["min_log"], tab["var_table"] = up(np.log(v)), up(v)
+        elif vt == ModelVarType.FIXED_SMALL:  # GD:302-305: variance is NOT exp(clipped log) at t = 0
+            tab["min_log"], tab["var_table"] = tab["posterior_log_variance_clipped"], up(self.posterior_variance)
+        else:  # LEARNED reads the log-variance straight from the model
             tab["min_log"] = tab["posterior_log_variance_clipped"]
         self._device_tables[key] = tab
         return tab

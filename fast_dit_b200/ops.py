@@ -246,7 +246,7 @@ def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_d
         _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
         _p(tables["min_log"]), _p(tables.get("max_log")),
         _p(outs["sample"]), _p(outs.get("pred_xstart")), _p(outs.get("mean")), _p(outs.get("log_variance")),
-        _p(outs.get("variance")), _p(tables.get("alphas_cumprod")), _p(tables.get("alphas_cumprod_prev")),
+        _p(outs.get("variance")), _p(tables.get("var_table")), _p(tables.get("alphas_cumprod")), _p(tables.get("alphas_cumprod_prev")),
         float(eta), int(sampler),
         B, Cc, HW, int(tables["posterior_mean_coef1"].numel()),
         mean_type, var_type, int(bool(clip_denoised)), int(cfg_half), int(n_cfg_ch), float(cfg_scale))

@@ -198,7 +198,8 @@ typedef struct ditb200_step_args {
   float* pred_xstart;    /* [B, C, HW] out or NULL */
   float* mean;           /* optional out */
   float* log_variance;   /* optional out */
-  float* variance;       /* optional out: exp(log_variance) */
+  float* variance;       /* optional out: var_table[t] if var_table != NULL, else exp(log_variance) */
+  const float* var_table; /* FIXED types: the variance table that goes with min_log (gaussian_diffusion.py:295-308) */
   /* DDIM only (sampler == DITB200_SAMPLER_DDIM): alphas_cumprod / alphas_cumprod_prev tables */
   const float* alphas_cumprod;
   const float* alphas_cumprod_prev;

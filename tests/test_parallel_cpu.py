@@ -1,0 +1,82 @@
+"""Multi-process (gloo, world_size 2, CPU) checks of the data-parallel host logic: the sampling
+shard plan of sample_ddp.py and the max-over-ranks timing reduction bench.py uses."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fast_dit_b200.parallel import ShardPlan, make_cfg_batch
+
+
+def test_shard_plan_matches_sample_ddp_arithmetic():
+    # 50 000 FID samples, 32 per GPU, 8 GPUs (sample_ddp.py defaults)
+    plans = [ShardPlan(8, r, 32, 50000) for r in range(8)]
+    p0 = plans[0]
+    assert p0.global_batch == 256 and p0.total_samples == 50176 and p0.samples_this_rank == 6272
+    assert p0.iterations == 196
+    idx = sorted(i for p in plans for i in p.all_indices())
+    assert idx == list(range(50176)), "ranks tile the index space exactly once"
+    assert [p.seed(3) for p in plans] == [24 + r for r in range(8)]
+    # index formula of sample_ddp.py:134-138: i * world + rank + total
+    assert plans[5].global_index(2, 7) == 7 * 8 + 5 + 2 * 256
+
+
+def test_cfg_batch_layout():
+    g = torch.Generator().manual_seed(0)
+    z, y = make_cfg_batch(3, 8, 1000, "cpu", generator=g)
+    assert z.shape == (6, 4, 8, 8) and torch.equal(z[:3], z[3:])
+    assert y.shape == (6,) and (y[3:] == 1000).all() and (y[:3] < 1000).all()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fast_dit_b200.parallel import init_from_env
+
+    r, local, w = init_from_env("gloo")
+    assert (r, w) == (rank, world) and dist.is_initialized()
+    plan = ShardPlan(w, r, 4, 20)
+    # every rank contributes its indices; together they must tile [0, total)
+    mine = torch.tensor(plan.all_indices(), dtype=torch.long)
+    gathered = [torch.empty_like(mine) for _ in range(w)]
+    dist.all_gather(gathered, mine)
+    allidx = torch.cat(gathered).sort().values
+    ok = torch.equal(allidx, torch.arange(plan.total_samples))
+    # rank-local RNG streams differ (seed = global_seed * world + rank)
+    torch.manual_seed(plan.seed(0))
+    draw = torch.randn(4)
+    draws = [torch.empty(4) for _ in range(w)]
+    dist.all_gather(draws, draw)
+    distinct = not torch.equal(draws[0], draws[1])
+    # timing reduction used by bench.py: the slowest rank defines the step time
+    t = torch.tensor([10.0 + 5.0 * r])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.barrier()
+    if r == 0:
+        q.put((ok, distinct, float(t.item()), plan.total_samples))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ok, distinct, tmax, total = q.get(timeout=10)
+    assert ok and distinct and tmax == 15.0 and total == 24
