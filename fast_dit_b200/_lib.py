@@ -14,7 +14,8 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libditb200.so"
 
 F32, BF16 = 0, 1
-EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RESID, EPI_BIAS_SILU = 0, 1, 2, 3
+ABI_VERSION = 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RESID, EPI_BIAS_SILU, EPI_MUL_DGELU = 0, 1, 2, 3, 4
 GEMM_TCGEN05, GEMM_FP32 = 0, 1
 MEAN_EPSILON, MEAN_START_X = 0, 1
 VAR_LEARNED_RANGE, VAR_LEARNED, VAR_FIXED = 0, 1, 2
@@ -29,6 +30,8 @@ class GemmArgs(C.Structure):
         ("gate_stride", _i), ("rows_per_gate", _i),
         ("M", _i), ("N", _i), ("K", _i),
         ("epilogue", _i), ("out_dtype", _i), ("engine", _i), ("tile_n", _i), ("cta_group", _i),
+        ("aux_out", _vp), ("aux_in", _vp), ("aux_dtype", _i), ("accumulate", _i), ("split_k", _i),
+        ("trans_a", _i), ("trans_w", _i),
     ]
 
 
@@ -69,10 +72,18 @@ SIGNATURES = {
     "ditb200_small_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_label_embed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
+    "ditb200_ln_modulate_bwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ditb200_gate_resid_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "ditb200_colsum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "ditb200_label_embed_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "ditb200_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ditb200_unpatchify_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ditb200_silu_bwd": (_i, [_vp, _vp, _vp, _i, _sz, _vp]),
     "ditb200_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "ditb200_cast_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "ditb200_silu_cast": (_i, [_vp, _vp, _i, _sz, _vp]),
     "ditb200_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ditb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ditb200_final_layer": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ditb200_cfg_combine": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ditb200_p_sample_step": (_i, [C.POINTER(StepArgs), _vp]),
@@ -107,7 +118,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.ditb200_abi_version() != 1:
+        if lib.ditb200_abi_version() != ABI_VERSION:
             raise Ditb200Error("libditb200 ABI version mismatch; rebuild")
         _lib = lib
     return _lib

@@ -1,0 +1,292 @@
+// backward.cu — the HBM-bound kernels of the training step's backward pass (a19 in SURVEY.md §8):
+// LayerNorm+modulate backward, gated-residual backward, column sums (bias gradients), the
+// embedding scatter, patchify / un-unpatchify layout kernels and SiLU'.  The contractions of the
+// backward pass (data and weight gradients) run on the tcgen05 GEMM with MN-major operands
+// (gemm_tc.cu); attention backward lives in attention.cu.
+#include "common.cuh"
+
+namespace ditb200 {
+
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 pk = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  uint2 pk;
+  pk.x = pack_bf16x2(v.x, v.y);
+  pk.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// ====================================================== LayerNorm + modulate, backward
+// h = xhat * (1 + scale[b]) + shift[b],  xhat = (x - mean) * rstd.
+//   dx      = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * (1 + scale[b])
+//   dshift[b] += sum_t dh,   dscale[b] += sum_t dh * xhat
+// CTA = kLnRows consecutive tokens of ONE image; one warp per row (lane owns float4 l + 32 j);
+// per-column partial sums of the CTA are combined in shared memory, then one atomic per column.
+constexpr int kLnRows = 32;
+template <typename TDh>
+__global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(
+    const TDh* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale, int mod_stride,
+    const float* __restrict__ stats, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
+    float* __restrict__ dscale, int dmod_stride, int T, int D) {
+  extern __shared__ float red[];  // [2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kLnRows;
+  const int t1 = min(T, t0 + kLnRows);
+  const int nv = D >> 2;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const float* sc = scale + (size_t)b * mod_stride;
+  const float invD = 1.0f / (float)D;
+  for (int t = t0 + warp; t < t1; t += 8) {
+    const size_t row = (size_t)b * T + t;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    const float* xr = x + row * D;
+    const TDh* dr = dh + row * D;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < nv; i += 32) {
+      const float4 xv = load4(xr + 4 * i), dv = load4(dr + 4 * i), cv = __ldg(reinterpret_cast<const float4*>(sc) + i);
+      const float g0 = dv.x * (1.f + cv.x), g1 = dv.y * (1.f + cv.y), g2 = dv.z * (1.f + cv.z), g3 = dv.w * (1.f + cv.w);
+      const float h0 = (xv.x - mean) * rstd, h1 = (xv.y - mean) * rstd, h2 = (xv.z - mean) * rstd, h3 = (xv.w - mean) * rstd;
+      s1 += (g0 + g1) + (g2 + g3);
+      s2 += (g0 * h0 + g1 * h1) + (g2 * h2 + g3 * h3);
+      atomicAdd(&red[4 * i + 0], dv.x), atomicAdd(&red[4 * i + 1], dv.y);
+      atomicAdd(&red[4 * i + 2], dv.z), atomicAdd(&red[4 * i + 3], dv.w);
+      atomicAdd(&red[D + 4 * i + 0], dv.x * h0), atomicAdd(&red[D + 4 * i + 1], dv.y * h1);
+      atomicAdd(&red[D + 4 * i + 2], dv.z * h2), atomicAdd(&red[D + 4 * i + 3], dv.w * h3);
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    float* dxr = dx + row * D;
+    for (int i = lane; i < nv; i += 32) {  // second pass: the row is in L1
+      const float4 xv = load4(xr + 4 * i), dv = load4(dr + 4 * i), cv = __ldg(reinterpret_cast<const float4*>(sc) + i);
+      float4 o;
+      o.x = rstd * (dv.x * (1.f + cv.x) - s1 - (xv.x - mean) * rstd * s2);
+      o.y = rstd * (dv.y * (1.f + cv.y) - s1 - (xv.y - mean) * rstd * s2);
+      o.z = rstd * (dv.z * (1.f + cv.z) - s1 - (xv.z - mean) * rstd * s2);
+      o.w = rstd * (dv.w * (1.f + cv.w) - s1 - (xv.w - mean) * rstd * s2);
+      if (accumulate) {
+        const float4 p = load4(dxr + 4 * i);
+        o.x += p.x, o.y += p.y, o.z += p.z, o.w += p.w;
+      }
+      store4(dxr + 4 * i, o);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dshift + (size_t)b * dmod_stride + i, red[i]);
+    atomicAdd(dscale + (size_t)b * dmod_stride + i, red[D + i]);
+  }
+}
+
+// ============================================================ gated residual, backward
+// x_out = x + gate[b] * y:  dy = dx_out * gate[b];  dgate[b] += sum_t dx_out * y;  dbias += sum_rows dy.
+// Thread = 4 columns, CTA = kGrRows tokens of one image: coalesced 128-bit row accesses, the
+// reductions over tokens stay in registers, one atomic per column per CTA.
+constexpr int kGrRows = 16;
+template <typename TY>
+__global__ void gate_resid_bwd_kernel(const float* __restrict__ dxo, const TY* __restrict__ y,
+                                      const float* __restrict__ gate, int gate_stride, TY* __restrict__ dy,
+                                      float* __restrict__ dgate, int dgate_stride, float* __restrict__ dbias, int T,
+                                      int D) {
+  const int b = blockIdx.y;
+  const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
+  if (c >= D) return;
+  const int t0 = blockIdx.x * kGrRows, t1 = min(T, t0 + kGrRows);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_stride + c));
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+  for (int t = t0; t < t1; ++t) {
+    const size_t off = ((size_t)b * T + t) * D + c;
+    const float4 d = load4(dxo + off), yy = load4(y + off);
+    const float4 o = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+    store4(dy + off, o);
+    ag.x += d.x * yy.x, ag.y += d.y * yy.y, ag.z += d.z * yy.z, ag.w += d.w * yy.w;
+    ab.x += o.x, ab.y += o.y, ab.z += o.z, ab.w += o.w;
+  }
+  float* dg = dgate + (size_t)b * dgate_stride + c;
+  atomicAdd(dg, ag.x), atomicAdd(dg + 1, ag.y), atomicAdd(dg + 2, ag.z), atomicAdd(dg + 3, ag.w);
+  if (dbias != nullptr)
+    atomicAdd(dbias + c, ab.x), atomicAdd(dbias + c + 1, ab.y), atomicAdd(dbias + c + 2, ab.z), atomicAdd(dbias + c + 3, ab.w);
+}
+
+// ======================================================================== column sums
+constexpr int kCsRows = 64;
+template <typename TIn>
+__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in, float* __restrict__ out, int R, int C) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * kCsRows, r1 = min(R, r0 + kCsRows);
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = r0; r < r1; ++r) {
+    const float4 v = load4(in + (size_t)r * C + c);
+    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+  }
+  atomicAdd(out + c, a.x), atomicAdd(out + c + 1, a.y), atomicAdd(out + c + 2, a.z), atomicAdd(out + c + 3, a.w);
+}
+
+// ================================================================ label embed, backward
+__global__ void label_embed_bwd_kernel(const float* __restrict__ dc, const int64_t* __restrict__ y,
+                                       float* __restrict__ dtable, int B, int D, int num_rows) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * D) return;
+  const int b = idx / D, d = idx - b * D;
+  long long row = y[b];
+  if (row < 0) row = 0;
+  if (row >= num_rows) row = num_rows - 1;
+  atomicAdd(dtable + (size_t)row * D + d, dc[idx]);
+}
+
+// ==================================================================== layout kernels
+// patches[(b,t), (c,i,j)] = x[b, c, hp*p + i, wp*p + j]: the im2col of the patch-embed conv, in the
+// flattened conv-weight order, bf16 (B operand of the patch-embed weight gradient).
+__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+                                int W, int p) {
+  const int Hp = H / p, Wp = W / p, K = C * p * p;
+  const size_t n = (size_t)B * Hp * Wp * K;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % K);
+    const size_t tok = idx / K;
+    const int t = (int)(tok % (Hp * Wp)), b = (int)(tok / (Hp * Wp));
+    const int hp = t / Wp, wp = t - hp * Wp;
+    const int c = k / (p * p), r = k - c * p * p;
+    const int i = r / p, j = r - i * p;
+    out[idx] = __float2bfloat16_rn(x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j]);
+  }
+}
+
+// dz[(b, h, w), (pi, pj, c)] = dout[b, c, h*p + pi, w*p + pj]: inverse of DiT.unpatchify's permutation
+// (models_original.py:228-230) applied to the gradient of the model output.
+__global__ void unpatchify_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dz, int B, int Cout,
+                                      int Hp, int p) {
+  const int NO = p * p * Cout, Himg = Hp * p;
+  const size_t n = (size_t)B * Hp * Hp * NO;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % NO);
+    const size_t tok = idx / NO;
+    const int t = (int)(tok % (Hp * Hp)), b = (int)(tok / (Hp * Hp));
+    const int h = t / Hp, w = t - h * Hp;
+    const int c = o % Cout, pq = o / Cout;
+    const int pi = pq / p, pj = pq - pi * p;
+    dz[idx] = __float2bfloat16_rn(dout[(((size_t)b * Cout + c) * Himg + h * p + pi) * Himg + w * p + pj]);
+  }
+}
+
+// dpre = dact * silu'(pre),  silu'(v) = s (1 + v (1 - s)),  s = sigmoid(v)
+__global__ void silu_bwd_kernel(const float* __restrict__ dact, const float* __restrict__ pre, float* __restrict__ out,
+                                int accumulate, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = pre[i];
+    const float s = 1.0f / (1.0f + expf(-v));
+    const float r = dact[i] * s * (1.0f + v * (1.0f - s));
+    out[i] = accumulate ? out[i] + r : r;
+  }
+}
+
+}  // namespace ditb200
+
+using namespace ditb200;
+
+extern "C" int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float* x, const float* scale,
+                                       int mod_stride, const float* stats, float* dx, int accumulate,
+                                       float* dshift, float* dscale, int dmod_stride, int B, int T, int D,
+                                       void* stream) {
+  DITB_REQUIRE(dh && x && scale && stats && dx && dshift && dscale, DITB200_EINVAL, "ln_modulate_bwd: null pointer");
+  DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0 && B <= 65535, DITB200_EINVAL, "ln_modulate_bwd: bad shape");
+  DITB_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(scale) && mod_stride % 4 == 0,
+               DITB200_EALIGN, "ln_modulate_bwd: misaligned pointer or stride");
+  dim3 grid((T + kLnRows - 1) / kLnRows, B);
+  const size_t smem = (size_t)2 * D * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dh_dtype == DITB200_BF16)
+    ln_modulate_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), x, scale,
+                                                                  mod_stride, stats, dx, accumulate, dshift, dscale,
+                                                                  dmod_stride, T, D);
+  else
+    ln_modulate_bwd_kernel<float><<<grid, 256, smem, st>>>(reinterpret_cast<const float*>(dh), x, scale, mod_stride,
+                                                          stats, dx, accumulate, dshift, dscale, dmod_stride, T, D);
+  DITB_LAUNCH_CHECK("ln_modulate_bwd");
+  return 0;
+}
+
+extern "C" int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_dtype, const float* gate,
+                                      int gate_stride, void* dy, int dy_dtype, float* dgate, int dgate_stride,
+                                      float* dbias, int B, int T, int D, void* stream) {
+  DITB_REQUIRE(dx_out && y && gate && dy && dgate, DITB200_EINVAL, "gate_resid_bwd: null pointer");
+  DITB_REQUIRE(y_dtype == dy_dtype, DITB200_EINVAL, "gate_resid_bwd: y and dy must share a dtype");
+  DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0 && B <= 65535, DITB200_EINVAL, "gate_resid_bwd: bad shape");
+  DITB_REQUIRE(aligned16(dx_out) && aligned16(y) && aligned16(dy) && aligned16(gate) && gate_stride % 4 == 0,
+               DITB200_EALIGN, "gate_resid_bwd: misaligned pointer or stride");
+  const int threads = 256;
+  dim3 grid((T + kGrRows - 1) / kGrRows, B, (D / 4 + threads - 1) / threads);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_dtype == DITB200_BF16)
+    gate_resid_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(
+        dx_out, reinterpret_cast<const __nv_bfloat16*>(y), gate, gate_stride, reinterpret_cast<__nv_bfloat16*>(dy),
+        dgate, dgate_stride, dbias, T, D);
+  else
+    gate_resid_bwd_kernel<float><<<grid, threads, 0, st>>>(dx_out, reinterpret_cast<const float*>(y), gate, gate_stride,
+                                                          reinterpret_cast<float*>(dy), dgate, dgate_stride, dbias, T, D);
+  DITB_LAUNCH_CHECK("gate_resid_bwd");
+  return 0;
+}
+
+extern "C" int ditb200_colsum(const void* in, int dtype, float* out, int accumulate, int R, int C, void* stream) {
+  DITB_REQUIRE(in && out, DITB200_EINVAL, "colsum: null pointer");
+  DITB_REQUIRE(R > 0 && C > 0 && C % 4 == 0, DITB200_EINVAL, "colsum: bad shape R=%d C=%d (C %% 4 == 0)", R, C);
+  DITB_REQUIRE(aligned16(in), DITB200_EALIGN, "colsum: misaligned input");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st);
+    if (e != cudaSuccess) return check_cuda(e, "colsum memset");
+  }
+  dim3 grid((C / 4 + 255) / 256, (R + kCsRows - 1) / kCsRows);
+  if (dtype == DITB200_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, R, C);
+  else
+    colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), out, R, C);
+  DITB_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+extern "C" int ditb200_label_embed_bwd(const float* dc, const int64_t* y, float* dtable, int B, int D, int num_rows,
+                                       void* stream) {
+  DITB_REQUIRE(dc && y && dtable && B > 0 && D > 0 && num_rows > 0, DITB200_EINVAL, "label_embed_bwd: bad argument");
+  const int n = B * D;
+  label_embed_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dc, y, dtable, B, D, num_rows);
+  DITB_LAUNCH_CHECK("label_embed_bwd");
+  return 0;
+}
+
+extern "C" int ditb200_patchify(const float* x, void* patches, int B, int C, int H, int W, int p, void* stream) {
+  DITB_REQUIRE(x && patches && B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0, DITB200_EINVAL,
+               "patchify: bad argument");
+  const size_t n = (size_t)B * C * H * W;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  patchify_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p);
+  DITB_LAUNCH_CHECK("patchify");
+  return 0;
+}
+
+extern "C" int ditb200_unpatchify_bwd(const float* dout, void* dz, int B, int Cout, int Hp, int p, void* stream) {
+  DITB_REQUIRE(dout && dz && B > 0 && Cout > 0 && Hp > 0 && p > 0, DITB200_EINVAL, "unpatchify_bwd: bad argument");
+  const size_t n = (size_t)B * Cout * Hp * p * Hp * p;
+  const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  unpatchify_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, reinterpret_cast<__nv_bfloat16*>(dz), B, Cout, Hp, p);
+  DITB_LAUNCH_CHECK("unpatchify_bwd");
+  return 0;
+}
+
+extern "C" int ditb200_silu_bwd(const float* dact, const float* pre, float* out, int accumulate, size_t n,
+                                void* stream) {
+  DITB_REQUIRE(dact && pre && out && n > 0, DITB200_EINVAL, "silu_bwd: bad argument");
+  const int blocks = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+  silu_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dact, pre, out, accumulate, n);
+  DITB_LAUNCH_CHECK("silu_bwd");
+  return 0;
+}

@@ -148,13 +148,16 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
 
 # ----------------------------------------------------------------------- GEMM
 def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
-         rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0):
-    """out = epilogue(a @ w.T).  a[M,K], w[N,K] both bf16 (tcgen05) or both f32 (check mode)."""
+         rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0,
+         aux_out=None, aux_in=None, accumulate: bool = False, split_k: int = 0, trans_a: bool = False,
+         trans_w: bool = False):
+    """out = epilogue(op(a) @ op(w).T).  a[M,K] (or [K,M] with trans_a), w[N,K] (or [K,N] with trans_w), both
+    bf16 (tcgen05) or both f32 (check mode, forward only)."""
     lib = _lib_for(a)
-    _chk_contig(a, w, bias, resid)
-    M, K = a.shape
-    N = w.shape[0]
-    assert w.shape[1] == K and a.dtype == w.dtype
+    _chk_contig(a, w, bias, resid, aux_out, aux_in)
+    K, M = a.shape if trans_a else a.shape[::-1]
+    Kw, N = w.shape if trans_w else w.shape[::-1]
+    assert Kw == K and a.dtype == w.dtype, (a.shape, w.shape, trans_a, trans_w)
     if engine is None:
         engine = L.GEMM_TCGEN05 if a.dtype == torch.bfloat16 else L.GEMM_FP32
     if epilogue == L.EPI_BIAS_GATE_RESID:
@@ -164,9 +167,13 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
         assert gate is not None and gate.stride(1) == 1
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
+    assert out.shape == (M, N) and out.is_contiguous()
+    aux = aux_out if aux_out is not None else aux_in
     args = L.GemmArgs(_p(a), _p(w), _p(bias), _p(out), _p(resid), _p(gate),
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
-                      _DT[out.dtype], engine, tile_n, cta_group)
+                      _DT[out.dtype], engine, tile_n, cta_group,
+                      _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
+                      int(trans_a), int(trans_w))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
           meta=2.0 * M * N * K)
     return out
@@ -285,3 +292,86 @@ def training_losses(model_out, x0, x_t, noise, t, tables, vb_scale: float = 1.0,
         int(tables["posterior_mean_coef1"].numel()))
     _call("training_losses", lib.ditb200_training_losses, C.byref(args), _stream())
     return {"mse": mse, "vb": vb, "loss": loss, "grad_model_out": grad}
+
+
+# ------------------------------------------------------------------- backward pass
+def ln_modulate_bwd(dh, x, scale, stats, T: int, dx, accumulate: bool, dshift, dscale):
+    """Backward of ln_modulate: dx (+)= d/dx, dshift/dscale ([B, D] views, common row stride) += sums over tokens."""
+    lib = _lib_for(x)
+    _chk_contig(dh, x, stats, dx)
+    M, D = x.shape
+    assert scale.stride(1) == 1 and dshift.stride(1) == 1 and dscale.stride(1) == 1 and dshift.stride(0) == dscale.stride(0)
+    _call("ln_modulate_bwd", lib.ditb200_ln_modulate_bwd, _p(dh), _DT[dh.dtype], _p(x), _p(scale), scale.stride(0),
+          _p(stats), _p(dx), int(accumulate), _p(dshift), _p(dscale), dshift.stride(0), M // T, T, D, _stream())
+    return dx
+
+
+def gate_resid_bwd(dx_out, y, gate, T: int, dgate, dbias=None, dy=None):
+    """dy = dx_out * gate[b]; dgate += sum_t dx_out * y; dbias += colsum(dy)."""
+    lib = _lib_for(dx_out)
+    _chk_contig(dx_out, y, dy, dbias)
+    M, D = dx_out.shape
+    if dy is None:
+        dy = torch.empty_like(y)
+    assert gate.stride(1) == 1 and dgate.stride(1) == 1
+    _call("gate_resid_bwd", lib.ditb200_gate_resid_bwd, _p(dx_out), _p(y), _DT[y.dtype], _p(gate), gate.stride(0),
+          _p(dy), _DT[dy.dtype], _p(dgate), dgate.stride(0), _p(dbias), M // T, T, D, _stream())
+    return dy
+
+
+def colsum(x, out=None, accumulate: bool = False):
+    lib = _lib_for(x)
+    _chk_contig(x, out)
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    _call("colsum", lib.ditb200_colsum, _p(x), _DT[x.dtype], _p(out), int(accumulate), R, Cc, _stream())
+    return out
+
+
+def label_embed_bwd(dc, y, dtable):
+    lib = _lib_for(dc)
+    y = y.to(torch.int64).contiguous()
+    _chk_contig(dc, dtable)
+    _call("label_embed_bwd", lib.ditb200_label_embed_bwd, _p(dc), _p(y), _p(dtable), dc.shape[0], dc.shape[1],
+          dtable.shape[0], _stream())
+    return dtable
+
+
+def patchify(x, p: int):
+    lib = _lib_for(x)
+    _chk_contig(x)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B * (H // p) * (W // p), Cc * p * p), device=x.device, dtype=torch.bfloat16)
+    _call("patchify", lib.ditb200_patchify, _p(x), _p(out), B, Cc, H, W, p, _stream())
+    return out
+
+
+def unpatchify_bwd(dout, p: int):
+    lib = _lib_for(dout)
+    _chk_contig(dout)
+    B, Cout, Himg, _ = dout.shape
+    hp = Himg // p
+    dz = torch.empty((B * hp * hp, p * p * Cout), device=dout.device, dtype=torch.bfloat16)
+    _call("unpatchify_bwd", lib.ditb200_unpatchify_bwd, _p(dout), _p(dz), B, Cout, hp, p, _stream())
+    return dz
+
+
+def silu_bwd(dact, pre, out=None, accumulate: bool = False):
+    lib = _lib_for(dact)
+    _chk_contig(dact, pre, out)
+    if out is None:
+        out = torch.empty_like(pre)
+    _call("silu_bwd", lib.ditb200_silu_bwd, _p(dact), _p(pre), _p(out), int(accumulate), pre.numel(), _stream())
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse, B: int, T: int, H: int, hd: int):
+    """dqkv[B*T, 3*H*hd] from the forward's qkv, out, lse and the gradient of out."""
+    lib = _lib_for(qkv)
+    _chk_contig(qkv, out, dout, lse)
+    dsum = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    _call("attention_bwd", lib.ditb200_attention_bwd, _p(qkv), _p(out), _p(dout), _p(lse), _p(dsum), _p(dqkv),
+          _DT[qkv.dtype], B, T, H, hd, _stream(), meta=10.0 * B * H * T * T * hd)
+    return dqkv

@@ -96,3 +96,59 @@ def init_from_env(backend: str = "nccl"):
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend, rank=rank, world_size=world)
     return rank, local, world
+
+
+class DataParallel(torch.nn.Module):
+    """Data-parallel training wrapper for this package's DiT: the role torch's
+    DistributedDataParallel plays in /root/reference/train_options/train_original.py:149 (cited TO:line).
+
+    Weights are replicated (broadcast from rank 0 at construction, like DDP's constructor); every rank
+    runs forward/backward on its own batch shard.  The model's backward writes gradients into one flat
+    arena (training.GradArena) and calls `_sync(bucket)` as soon as a bucket — the final layer, each
+    DiT block from last to first, the embedders — is complete; the bucket's contiguous slice is
+    all-reduced (mean) asynchronously, so NCCL traffic over NVLink overlaps the rest of backward.  The
+    compute stream waits for all collectives only at the end of backward."""
+
+    def __init__(self, module, process_group=None, broadcast_parameters: bool = True):
+        super().__init__()
+        import torch.distributed as dist
+
+        self.module = module
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._pending = []
+        self.buckets_issued = []  # bucket keys in the order they were reduced (inspection / tests)
+        if self.world > 1 and broadcast_parameters:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=0, group=process_group)
+        module._grad_sync = self._sync
+
+    def _sync(self, key, arena):
+        import torch.distributed as dist
+
+        if key is None:  # end of backward: the compute stream must see every reduced bucket
+            for work, buf, avg_done in self._pending:
+                work.wait()
+                if not avg_done:
+                    buf.div_(self.world)
+            self._pending = []
+            return
+        self.buckets_issued.append(key)
+        if self.world == 1:
+            return
+        buf = arena.bucket(key)
+        if buf.is_cuda:  # NCCL averages in the collective
+            self._pending.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True), buf, True))
+        else:            # gloo (CPU tests of the host logic): sum, divide afterwards
+            self._pending.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), buf, False))
+
+    def forward(self, *args, **kwargs):
+        self.buckets_issued = []
+        return self.module(*args, **kwargs)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(self.module, name)

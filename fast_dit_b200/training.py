@@ -1,0 +1,276 @@
+"""Training step of the DiT denoiser on libditb200: forward that keeps what backward needs, and a
+hand-sequenced backward whose every kernel is a C-ABI entry point.
+
+The reference gets this path from torch.autograd over ~600 ATen/cuBLAS kernels per forward
+(train_options/train_original.py:206-209 -> models_original.py:233-248).  Here one
+torch.autograd.Function spans the whole model: PyTorch only links it into the graph between the
+diffusion loss (autograd.py) and the parameters; the arithmetic is
+
+  forward   the inference kernel sequence, with the GEMM epilogues also writing the pre-GELU
+            activation and the un-gated branch outputs (aux_out), LayerNorm statistics and the
+            attention log-sum-exp;
+  backward  per block, in reverse: gated-residual backward -> weight gradient (tokens contracted on
+            the tensor cores straight from the row-major activations, MN-major operands) -> data
+            gradient (with GELU' fused into the epilogue) -> LayerNorm+modulate backward -> flash
+            attention backward -> adaLN backward; bias gradients by column sums.
+
+Gradients are written into one flat f32 arena laid out in `parameters()` order, so a data-parallel
+wrapper (parallel.DataParallel) can all-reduce each block's contiguous slice as soon as that block's
+backward is done, overlapping NCCL with the rest of backward (train_original.py:149's DDP).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+# ------------------------------------------------------------------ gradient arena
+class GradArena:
+    """One flat f32 buffer holding every trainable parameter's gradient, in `parameters()` order.
+
+    Buckets are contiguous slices: the embedders, each DiT block, the final layer — the order in which
+    backward completes them is final layer, blocks L-1..0, embedders."""
+
+    ALIGN = 64  # floats: every gradient starts on a 256-byte boundary (vector atomics / TMA-free stores)
+
+    def __init__(self, model):
+        self.offsets = {}
+        off = 0
+        self.bucket_ranges = {}
+        names = dict((id(p), n) for n, p in model.named_parameters())
+        for p in model.parameters():
+            if not p.requires_grad:
+                continue
+            n = names[id(p)]
+            key = n.split(".")[0] + ("." + n.split(".")[1] if n.startswith("blocks.") else "")
+            if key in ("x_embedder", "t_embedder", "y_embedder"):
+                key = "embed"
+            start = off
+            self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            lo, hi = self.bucket_ranges.get(key, (start, start))
+            self.bucket_ranges[key] = (min(lo, start), off)
+        self.total = off
+        dev = next(model.parameters()).device
+        self.flat = torch.zeros(self.total, device=dev, dtype=torch.float32)
+
+    def view(self, p):
+        off, n, shape = self.offsets[id(p)]
+        return self.flat[off:off + n].view(shape)
+
+    def bucket(self, key):
+        lo, hi = self.bucket_ranges[key]
+        return self.flat[lo:hi]
+
+    def aliases(self, p):
+        g = p.grad
+        return g is not None and g.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[id(p)][0]
+
+
+def _arena_for(model):
+    """Reuse the model's arena unless a parameter's .grad still lives in it (the caller is accumulating
+    gradients across backward calls): then this backward gets a scratch arena and autograd adds."""
+    dev = next(model.parameters()).device
+    ar = getattr(model, "_grad_arena", None)
+    if ar is None or ar.flat.device != dev:
+        ar = GradArena(model)
+        model._grad_arena = ar
+        return ar
+    if getattr(model, "_grad_sync", None) is None and any(ar.aliases(p) for p in model.parameters() if p.requires_grad):
+        return GradArena(model)
+    return ar
+
+
+def _split_k(M, N, K, trans_w):
+    """Work units per tile for a long-K GEMM: fill the machine when there are few output tiles (weight
+    gradients contract over all tokens; the adaLN data gradient has M = batch)."""
+    cg = 2 if M > 128 else 1
+    bn = 256 if N > 192 else (256 if (N > 128 and trans_w) else 192 if N > 128 else 128)
+    tiles = math.ceil(M / (128 * cg)) * math.ceil(N / bn)
+    ctas = 148 // cg
+    kb = math.ceil(K / 64)
+    best, best_cost = 1, None
+    for s in range(1, min(32, kb) + 1):
+        waves = math.ceil(tiles * s / ctas)
+        cost = waves / s * (1.0 + 0.03 * (s - 1))  # atomics + shorter main loops are not free
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s, cost
+    return best
+
+
+def _wgrad(dy, x, out):
+    """out[Nout, Kin] = dy[tokens, Nout]^T @ x[tokens, Kin] on the tensor cores (no transposed copies)."""
+    Mo, No, K = dy.shape[1], x.shape[1], dy.shape[0]
+    return ops.gemm(dy, x, None, out=out, trans_a=True, trans_w=True, split_k=_split_k(Mo, No, K, True))
+
+
+def _dgrad(dy, w, **kw):
+    """dx[tokens, Kin] = dy[tokens, Nout] @ w[Nout, Kin]."""
+    return ops.gemm(dy, w, None, trans_w=True, **kw)
+
+
+class _DiTFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, t, y, *params):
+        if model.precision != "bf16":
+            raise L.Ditb200Error("training runs in bf16 (tcgen05) only; the fp32 check mode is forward-only")
+        sh = model._shadows()
+        D, Hh, p, Ld = model.hidden_size, model.num_heads, model.patch_size, model.depth
+        hd = D // Hh
+        x = x.float().contiguous()
+        N = x.shape[0]
+        T = (x.shape[2] // p) * (x.shape[3] // p)
+        M = N * T
+        dev = x.device
+        if model.pos_embed.shape[1] != T:
+            raise L.Ditb200Error(f"input grid gives {T} tokens but pos_embed has {model.pos_embed.shape[1]}")
+        tok = ops.patch_embed(x, model.x_embedder.proj.weight, model.x_embedder.proj.bias, model.pos_embed, p)
+        # conditioning (models_original.py:241-243), keeping the SiLU pre-activations
+        te, ye = model.t_embedder, model.y_embedder
+        t_freq = ops.timestep_embedding(t, te.frequency_embedding_size)
+        pre1 = ops.small_linear(t_freq, te.mlp[0].weight, te.mlp[0].bias)
+        h1 = ops.silu_cast(pre1, torch.float32)
+        y_idx = ye.token_drop(y) if (model.training and ye.dropout_prob > 0) else y
+        y_emb = ops.label_embed(y_idx, ye.embedding_table.weight)
+        c = ops.small_linear(h1, te.mlp[2].weight, te.mlp[2].bias, add=y_emb)
+        sc = ops.silu_cast(c, torch.bfloat16)
+        mod = ops.gemm(sc, sh["ada_w"], sh["ada_b"], out_dtype=torch.float32)
+        w = sh["w"]
+        saved = []
+        bf = torch.bfloat16
+        for i, blk in enumerate(model.blocks):
+            m = mod[:, i * 6 * D:(i + 1) * 6 * D]
+            sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * D:(j + 1) * D] for j in range(6))
+            st1 = torch.empty((M, 2), device=dev, dtype=torch.float32)
+            hA = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=bf, stats=st1)
+            qkv = ops.gemm(hA, w[4 * i], blk.attn.qkv.bias)
+            lse = torch.empty((N, Hh, T), device=dev, dtype=torch.float32)
+            o = ops.attention(qkv, N, T, Hh, hd, lse=lse)
+            y1 = torch.empty((M, D), device=dev, dtype=bf)
+            x_mid = torch.empty_like(tok)
+            ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
+                     rows_per_gate=T, out=x_mid, aux_out=y1)
+            st2 = torch.empty((M, 2), device=dev, dtype=torch.float32)
+            hB = ops.ln_modulate(x_mid, sh2, sc2, T, out_dtype=bf, stats=st2)
+            a1 = torch.empty((M, w[4 * i + 2].shape[0]), device=dev, dtype=bf)
+            u = ops.gemm(hB, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU, aux_out=a1)
+            y2 = torch.empty((M, D), device=dev, dtype=bf)
+            x_out = torch.empty_like(tok)
+            ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x_mid, gate=g2,
+                     rows_per_gate=T, out=x_out, aux_out=y2)
+            saved.append((tok, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2))
+            tok = x_out
+        mf = mod[:, Ld * 6 * D:]
+        fl = model.final_layer
+        out = ops.final_layer(tok, mf[:, :D], mf[:, D:], fl.linear.weight, fl.linear.bias, T, p, model.out_channels)
+        ctx.model = model
+        ctx.saved = saved
+        ctx.misc = (x, t_freq, pre1, h1, y_idx, c, sc, mod, tok, N, T)
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model = ctx.model
+        sh = model._shadows()
+        x, t_freq, pre1, h1, y_idx, c, sc, mod, tok_final, N, T = ctx.misc
+        D, Hh, p, Ld = model.hidden_size, model.num_heads, model.patch_size, model.depth
+        hd = D // Hh
+        dev = x.device
+        bf = torch.bfloat16
+        arena = _arena_for(model)
+        G = arena.view
+        sync = getattr(model, "_grad_sync", None)  # parallel.DataParallel: called as each bucket completes
+        w = sh["w"]
+        ada_w = sh["ada_w"]
+        dsc = torch.zeros((N, D), device=dev, dtype=torch.float32)  # gradient of silu(c), summed over all adaLN layers
+
+        def ada_bwd(dmod, w_rows, lin):
+            """adaLN_modulation[1] backward: weight/bias gradients and the contribution to d silu(c)."""
+            dmod_bf = ops.cast_bf16(dmod)
+            ops.gemm(dmod_bf, sc, None, out=G(lin.weight), trans_a=True, trans_w=True)
+            ops.colsum(dmod, out=G(lin.bias))
+            ops.gemm(dmod_bf, w_rows, None, out=dsc, trans_w=True, accumulate=True,
+                     split_k=_split_k(N, D, dmod.shape[1], True))
+
+        # ---------------- final layer (models_original.py:138-142, 218-231)
+        fl = model.final_layer
+        mf = mod[:, Ld * 6 * D:]
+        dz = ops.unpatchify_bwd(dout.float().contiguous(), p)
+        stf = torch.empty((N * T, 2), device=dev, dtype=torch.float32)
+        hf = ops.ln_modulate(tok_final, mf[:, :D], mf[:, D:], T, out_dtype=bf, stats=stf)
+        _wgrad(dz, hf, G(fl.linear.weight))
+        ops.colsum(dz, out=G(fl.linear.bias))
+        dhf = _dgrad(dz, ops.cast_bf16(fl.linear.weight.detach()))
+        dmod_f = torch.zeros((N, 2 * D), device=dev, dtype=torch.float32)
+        dtok = torch.empty((N * T, D), device=dev, dtype=torch.float32)
+        ops.ln_modulate_bwd(dhf, tok_final, mf[:, D:], stf, T, dtok, False, dmod_f[:, :D], dmod_f[:, D:])
+        ada_bwd(dmod_f, ada_w[Ld * 6 * D:], fl.adaLN_modulation[1])
+        del dz, hf, dhf
+        if sync is not None:
+            sync("final_layer", arena)
+
+        # ---------------- blocks, last to first (models_original.py:118-122)
+        for i in range(Ld - 1, -1, -1):
+            blk = model.blocks[i]
+            x_in, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2 = ctx.saved[i]
+            ctx.saved[i] = None
+            m = mod[:, i * 6 * D:(i + 1) * 6 * D]
+            sc1, g1, sc2, g2 = m[:, D:2 * D], m[:, 2 * D:3 * D], m[:, 4 * D:5 * D], m[:, 5 * D:6 * D]
+            dmod = torch.zeros((N, 6 * D), device=dev, dtype=torch.float32)
+            dm = [dmod[:, j * D:(j + 1) * D] for j in range(6)]
+            # x_out = x_mid + g2 * fc2(gelu(fc1(modulate(LN(x_mid)))))
+            gb = G(blk.mlp.fc2.bias).zero_()
+            dy2 = ops.gate_resid_bwd(dtok, y2, g2, T, dm[5], dbias=gb)
+            _wgrad(dy2, u, G(blk.mlp.fc2.weight))
+            da1 = _dgrad(dy2, w[4 * i + 3], epilogue=L.EPI_MUL_DGELU, aux_in=a1)
+            _wgrad(da1, hB, G(blk.mlp.fc1.weight))
+            ops.colsum(da1, out=G(blk.mlp.fc1.bias))
+            dh = _dgrad(da1, w[4 * i + 2])
+            ops.ln_modulate_bwd(dh, x_mid, sc2, st2, T, dtok, True, dm[3], dm[4])
+            del dy2, da1, dh, y2, u, a1, hB
+            # x_mid = x_in + g1 * proj(attention(qkv(modulate(LN(x_in)))))
+            gb = G(blk.attn.proj.bias).zero_()
+            dy1 = ops.gate_resid_bwd(dtok, y1, g1, T, dm[2], dbias=gb)
+            _wgrad(dy1, o, G(blk.attn.proj.weight))
+            do = _dgrad(dy1, w[4 * i + 1])
+            dqkv = ops.attention_bwd(qkv, o, do, lse, N, T, Hh, hd)
+            _wgrad(dqkv, hA, G(blk.attn.qkv.weight))
+            ops.colsum(dqkv, out=G(blk.attn.qkv.bias))
+            dh = _dgrad(dqkv, w[4 * i])
+            ops.ln_modulate_bwd(dh, x_in, sc1, st1, T, dtok, True, dm[0], dm[1])
+            ada_bwd(dmod, ada_w[i * 6 * D:(i + 1) * 6 * D], blk.adaLN_modulation[1])
+            del dy1, do, dqkv, dh
+            if sync is not None:
+                sync(f"blocks.{i}", arena)
+
+        # ---------------- embedders (models_original.py:240-243)
+        pe = model.x_embedder.proj
+        _wgrad(ops.cast_bf16(dtok), ops.patchify(x, p), G(pe.weight).view(D, -1))
+        ops.colsum(dtok, out=G(pe.bias))
+        dc = ops.silu_bwd(dsc, c)
+        te, ye = model.t_embedder, model.y_embedder
+        ops.label_embed_bwd(dc, y_idx, G(ye.embedding_table.weight).zero_())
+        dc_bf = ops.cast_bf16(dc)
+        ops.gemm(dc_bf, ops.cast_bf16(h1), None, out=G(te.mlp[2].weight), trans_a=True, trans_w=True)
+        ops.colsum(dc, out=G(te.mlp[2].bias))
+        dh1 = _dgrad(dc_bf, ops.cast_bf16(te.mlp[2].weight.detach()), out_dtype=torch.float32)
+        dpre = ops.silu_bwd(dh1, pre1)
+        ops.gemm(ops.cast_bf16(dpre), ops.cast_bf16(t_freq), None, out=G(te.mlp[0].weight), trans_a=True, trans_w=True)
+        ops.colsum(dpre, out=G(te.mlp[0].bias))
+        if sync is not None:
+            sync("embed", arena)
+            sync(None, arena)  # all buckets issued: make the compute stream wait for the collectives
+
+        grads = [arena.view(q) if q.requires_grad else None for q in model.parameters()]
+        assert len(grads) == ctx.n_params
+        return (None, None, None, None, *grads)
+
+
+def dit_forward_train(model, x, t, y):
+    """DiT.forward with autograd: returns the model output wired to every parameter's gradient."""
+    return _DiTFunction.apply(model, x, t, y, *model.parameters())

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DITB200_ABI_VERSION 1
+#define DITB200_ABI_VERSION 2
 
 #define DITB200_F32 0
 #define DITB200_BF16 1
@@ -44,6 +44,7 @@ extern "C" {
 #define DITB200_EPI_BIAS_GELU 1       /* out = gelu_tanh(acc + bias)                   */
 #define DITB200_EPI_BIAS_GATE_RESID 2 /* out_f32 = resid + gate[row/T] * (acc + bias)  */
 #define DITB200_EPI_BIAS_SILU 3       /* out = silu(acc + bias)                        */
+#define DITB200_EPI_MUL_DGELU 4       /* out = (acc + bias) * gelu_tanh'(aux_in)  (backward of fc1's GELU) */
 
 /* GEMM engines */
 #define DITB200_GEMM_TCGEN05 0 /* bf16 operands, tcgen05.mma + TMEM accumulators, TMA-fed */
@@ -116,6 +117,44 @@ int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, 
                         void* out, int out_dtype, float* stats, int B, int T, int D, float eps,
                         void* stream);
 
+/* Backward of ditb200_ln_modulate with respect to x, shift and scale.
+ * dh[B*T, D] (dh_dtype) is the gradient of the modulated output; x, scale, stats as in the forward.
+ * dx[B*T, D] f32 receives the gradient wrt x (added to dx when accumulate != 0: the residual stream's
+ * gradient flows through both the branch and the skip connection).  dshift/dscale [B, D] f32 (row stride
+ * dmod_stride) are ACCUMULATED with atomics: the caller zeroes them once per step. */
+int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float* x, const float* scale, int mod_stride,
+                            const float* stats, float* dx, int accumulate, float* dshift, float* dscale,
+                            int dmod_stride, int B, int T, int D, void* stream);
+
+/* Backward of the gated-residual epilogue x_out = x + gate[b] * y (models_original.py:120-121):
+ * dy[B*T, D] (dy_dtype == y_dtype) = dx_out * gate[b];  dgate[b, :] += sum_t dx_out[b,t,:] * y[b,t,:];
+ * dbias[:] += sum over all tokens of dy (the bias gradient of the Linear that produced y; may be NULL).
+ * dgate / dbias are ACCUMULATED with atomics: the caller zeroes them once per step.
+ * dx_out itself is also the gradient of the skip path and is left untouched. */
+int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_dtype, const float* gate, int gate_stride,
+                           void* dy, int dy_dtype, float* dgate, int dgate_stride, float* dbias, int B, int T,
+                           int D, void* stream);
+
+/* out[C] f32 (+)= column sums of in[R, C] (dtype): bias gradients of the QKV / fc1 / embedding Linears.
+ * C % 4 == 0.  accumulate == 0 zeroes out first. */
+int ditb200_colsum(const void* in, int dtype, float* out, int accumulate, int R, int C, void* stream);
+
+/* dtable[y[b], :] += dc[b, :] (f32 atomics): backward of the label-embedding gather. */
+int ditb200_label_embed_bwd(const float* dc, const int64_t* y, float* dtable, int B, int D, int num_rows,
+                            void* stream);
+
+/* patches[B*T, C*p*p] bf16 = im2col of x[B,C,H,W] f32 in the conv-weight order (c, i, j): the
+ * token-major operand of the patch-embed weight gradient (backward of timm PatchEmbed.proj). */
+int ditb200_patchify(const float* x, void* patches, int B, int C, int H, int W, int p, void* stream);
+
+/* dz[B*T, p*p*Cout] bf16 = inverse of DiT.unpatchify (models_original.py:218-231) applied to the
+ * gradient dout[B, Cout, Hp*p, Hp*p] f32 of the model output; T = Hp*Hp. */
+int ditb200_unpatchify_bwd(const float* dout, void* dz, int B, int Cout, int Hp, int p, void* stream);
+
+/* out (+)= dact * silu'(pre), elementwise f32: backward of the nn.SiLU in TimestepEmbedder.mlp and in
+ * front of every adaLN_modulation Linear (models_original.py:35,114,135). */
+int ditb200_silu_bwd(const float* dact, const float* pre, float* out, int accumulate, size_t n, void* stream);
+
 /* ----------------------------------------------------------------- GEMMs */
 
 typedef struct ditb200_gemm_args {
@@ -133,12 +172,27 @@ typedef struct ditb200_gemm_args {
   int engine;    /* DITB200_GEMM_* */
   int tile_n;    /* TCGEN05 only: output-tile width 128/192/256, 0 = choose from the shape */
   int cta_group; /* TCGEN05 only: 1 = one CTA per tile, 2 = CTA pair (256-row tile), 0 = choose */
+  /* --- training extras (all optional, zero = off) --- */
+  void* aux_out;       /* [M, N], dtype aux_dtype: the pre-epilogue value acc + bias.  With EPI_BIAS_GELU this
+                          is fc1's pre-activation, with EPI_BIAS_GATE_RESID the un-gated branch output; both
+                          are what the backward pass needs and the fused forward would otherwise discard */
+  const void* aux_in;  /* [M, N], dtype aux_dtype: EPI_MUL_DGELU's pre-activation */
+  int aux_dtype;
+  int accumulate;      /* out += result instead of out = result (f32 out, plain EPI_BIAS; f32 vector atomics) */
+  int split_k;         /* TCGEN05: split the K loop over this many work units per tile, combined with f32 atomics
+                          (f32 out, plain EPI_BIAS; out is zeroed first unless accumulate != 0); 0/1 = off */
+  int trans_a;         /* TCGEN05: a is stored [K, M] row-major and read as an MN-major operand */
+  int trans_w;         /* TCGEN05: w is stored [K, N] row-major and read as an MN-major operand.
+                          data gradient   dX[M,Kin]    = dY[M,Nout] . W[Nout,Kin]      -> trans_w
+                          weight gradient dW[Nout,Kin] = dY[tokens,Nout]^T . X[tokens,Kin] -> trans_a + trans_w */
 } ditb200_gemm_args;
 
 /* out = epilogue(a · wᵀ).  Replaces, per DiTBlock: timm Attention.qkv (EPI_BIAS),
  * Attention.proj + `x + gate_msa * (.)` (EPI_BIAS_GATE_RESID; models_original.py:120),
  * Mlp.fc1 + GELU(tanh) (EPI_BIAS_GELU; :110-112), Mlp.fc2 + `x + gate_mlp * (.)` (:121).
- * TCGEN05 engine: K % 64 == 0, N % 16 == 0, pointers 16-byte aligned. */
+ * The backward pass runs its data and weight gradients through the same entry point with trans_a /
+ * trans_w (autograd's addmm backward in the reference).
+ * TCGEN05 engine: N % 8 == 0; K % 8 == 0 unless both operands are transposed; pointers 16-byte aligned. */
 int ditb200_gemm(const ditb200_gemm_args* args, void* stream);
 
 /* f32 → bf16 cast of a contiguous array (weight shadows). n elements. */
@@ -158,6 +212,12 @@ int ditb200_silu_cast(const float* in, void* out, int out_dtype, size_t n, void*
  * dtype.  lse (optional, f32 [B,H,T]) receives log-sum-exp rows for backward. */
 int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
                           int hd, void* stream);
+
+/* Backward of ditb200_attention_fwd.  qkv/out/dout/dqkv in `dtype`; lse f32 [B,H,T] from the forward;
+ * dsum f32 [B,H,T] is caller-owned scratch (row sums of dout*out).  dqkv[B*T, 3*H*hd] is written in
+ * full (dQ | dK | dV in the forward's column layout), ready to be the dY of the QKV GEMM's backward. */
+int ditb200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                          float* dsum, void* dqkv, int dtype, int B, int T, int H, int hd, void* stream);
 
 /* ----------------------------------------------------------- final layer */
 

@@ -1,0 +1,301 @@
+"""Backward pass on the GPU: each backward kernel against torch autograd of the same fp32 op, then the
+whole training step (model gradients, diffusion loss) against the CPU oracle's autograd."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from fast_dit_b200 import ops as o
+
+    return o
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------- GEMM variants
+@pytest.mark.parametrize("ta,tw", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(512, 384, 256), (1152, 1152, 2048), (32, 1152, 1024), (384, 16, 1024),
+                                   (2304, 384, 32), (300 * 8, 520, 200)])
+def test_gemm_transposed_operands(ops, dev, ta, tw, M, N, K):
+    if not (ta and tw) and K % 8:
+        pytest.skip("K-major operands need K % 8 == 0")
+    g = _g(1)
+    A = torch.randn(M, K, device=dev, generator=g)
+    W = torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)
+    a = (A.t().contiguous() if ta else A).bfloat16()
+    w = (W.t().contiguous() if tw else W).bfloat16()
+    ref = (a.double().t() if ta else a.double()) @ (w.double() if tw else w.double().t())
+    y = ops.gemm(a, w, None, out_dtype=torch.float32, trans_a=ta, trans_w=tw)
+    assert rel_l2(y, ref) < 2e-5
+    # split-K and accumulate on top of an existing value
+    base = torch.randn(M, N, device=dev, generator=g)
+    y2 = ops.gemm(a, w, None, out=base.clone(), trans_a=ta, trans_w=tw, split_k=3, accumulate=True)
+    assert rel_l2(y2, ref + base.double()) < 2e-5
+    y3 = ops.gemm(a, w, None, out_dtype=torch.float32, trans_a=ta, trans_w=tw, split_k=4)
+    assert rel_l2(y3, ref) < 2e-5
+
+
+@pytest.mark.parametrize("cg,bn", [(1, 128), (1, 256), (2, 128), (2, 256), (1, 192)])
+def test_gemm_transposed_tiles(ops, dev, cg, bn):
+    g = _g(2)
+    M, N, K = 768, 640, 512
+    a = torch.randn(K, M, device=dev, generator=g).bfloat16()
+    w = (torch.randn(K, N, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    ref = a.double().t() @ w.double()
+    y = ops.gemm(a, w, None, out_dtype=torch.float32, trans_a=True, trans_w=True, tile_n=bn, cta_group=cg)
+    assert rel_l2(y, ref) < 2e-5
+
+
+def test_gemm_aux_out_and_dgelu(ops, dev):
+    from fast_dit_b200 import _lib as L
+
+    g = _g(3)
+    M, N, K = 1024, 1536, 384
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device=dev, generator=g)
+    pre_ref = a.double() @ w.double().t() + b.double()
+    aux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    u = ops.gemm(a, w, b, epilogue=L.EPI_BIAS_GELU, aux_out=aux)
+    assert rel_l2(aux.float(), pre_ref) < 4e-3
+    assert rel_l2(u.float(), F.gelu(pre_ref, approximate="tanh")) < 4e-3
+    # gated residual keeps the un-gated branch
+    T = 64
+    resid = torch.randn(M, N, device=dev, generator=g)
+    gate = torch.randn(M // T, N, device=dev, generator=g)
+    aux2 = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    out = torch.empty_like(resid)
+    ops.gemm(a, w, b, epilogue=L.EPI_BIAS_GATE_RESID, resid=resid, gate=gate, rows_per_gate=T, out=out, aux_out=aux2)
+    assert rel_l2(aux2.float(), pre_ref) < 4e-3
+    assert rel_l2(out, resid.double() + gate.double().repeat_interleave(T, 0) * pre_ref) < 1e-5
+    # data gradient through GELU: dpre = (dy @ W2) * gelu'(pre)
+    dy = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w2 = (torch.randn(K, N, device=dev, generator=g) / math.sqrt(K)).bfloat16()  # fc2.weight [out=K, in=N]
+    pre = aux.float().double().requires_grad_(True)
+    F.gelu(pre, approximate="tanh").backward(dy.double() @ w2.double())
+    got = ops.gemm(dy, w2, None, trans_w=True, epilogue=L.EPI_MUL_DGELU, aux_in=aux)
+    assert rel_l2(got.float(), pre.grad) < 5e-3
+
+
+# ---------------------------------------------------------------------- elementwise backward
+@pytest.mark.parametrize("D,T", [(384, 37), (1152, 256), (768, 64)])
+@pytest.mark.parametrize("dh_dtype", [torch.float32, torch.bfloat16])
+def test_ln_modulate_bwd(ops, dev, D, T, dh_dtype):
+    g = _g(4)
+    B = 3
+    x = (torch.randn(B * T, D, device=dev, generator=g) * 2 + 0.3)
+    mod = torch.randn(B, 6 * D, device=dev, generator=g) * 0.5
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    dh = torch.randn(B * T, D, device=dev, generator=g).to(dh_dtype)
+    stats = torch.empty(B * T, 2, device=dev)
+    ops.ln_modulate(x, shift, scale, T, out_dtype=torch.float32, stats=stats)
+    xd = x.double().requires_grad_(True)
+    sd = shift.double().clone().requires_grad_(True)
+    cd = scale.double().clone().requires_grad_(True)
+    h = F.layer_norm(xd, (D,), eps=1e-6).view(B, T, D) * (1 + cd[:, None]) + sd[:, None]
+    h.backward(dh.double().view(B, T, D))
+    prev = torch.randn(B * T, D, device=dev, generator=g)
+    dmod = torch.zeros(B, 6 * D, device=dev)
+    dx = ops.ln_modulate_bwd(dh, x, scale, stats, T, prev.clone(), True, dmod[:, :D], dmod[:, D:2 * D])
+    assert rel_l2(dx, xd.grad + prev.double()) < 2e-5
+    assert rel_l2(dmod[:, :D], sd.grad) < 2e-5
+    assert rel_l2(dmod[:, D:2 * D], cd.grad) < 2e-5
+    dx2 = ops.ln_modulate_bwd(dh, x, scale, stats, T, torch.empty_like(x), False, dmod[:, :D], dmod[:, D:2 * D])
+    assert rel_l2(dx2, xd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("D,T", [(384, 37), (1152, 256)])
+def test_gate_resid_bwd(ops, dev, D, T):
+    g = _g(5)
+    B = 3
+    dxo = torch.randn(B * T, D, device=dev, generator=g)
+    y = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+    mod = torch.randn(B, 6 * D, device=dev, generator=g)
+    gate = mod[:, 2 * D:3 * D]
+    dmod = torch.zeros(B, 6 * D, device=dev)
+    dbias = torch.zeros(D, device=dev)
+    dy = ops.gate_resid_bwd(dxo, y, gate, T, dmod[:, 2 * D:3 * D], dbias=dbias)
+    ref_dy = dxo.double().view(B, T, D) * gate.double()[:, None]
+    assert rel_l2(dy.float(), ref_dy.view(B * T, D)) < 4e-3
+    assert rel_l2(dmod[:, 2 * D:3 * D], (dxo.double() * y.double()).view(B, T, D).sum(1)) < 1e-5
+    assert rel_l2(dbias, ref_dy.sum((0, 1))) < 1e-5
+    assert float(dmod[:, :2 * D].abs().max()) == 0.0
+
+
+def test_small_backward_kernels(ops, dev):
+    g = _g(6)
+    x = torch.randn(1000, 520, device=dev, generator=g)
+    assert rel_l2(ops.colsum(x), x.double().sum(0)) < 1e-5
+    xb = x.bfloat16()
+    acc = torch.ones(520, device=dev)
+    assert rel_l2(ops.colsum(xb, out=acc, accumulate=True), xb.double().sum(0) + 1) < 1e-5
+    # patchify = im2col in conv-weight order: conv2d(x, w) == patches @ w.flatten(1).T
+    for p, H in [(2, 32), (4, 32), (8, 32)]:
+        img = torch.randn(3, 4, H, H, device=dev, generator=g)
+        w = torch.randn(24, 4, p, p, device=dev, generator=g)
+        ref = F.conv2d(img, w, stride=p).flatten(2).transpose(1, 2).reshape(-1, 24)
+        got = ops.patchify(img, p).float() @ w.flatten(1).t()
+        assert rel_l2(got, ref) < 5e-3
+        # unpatchify_bwd is the inverse permutation of DiT.unpatchify
+        c = 8
+        z = torch.randn(3, (H // p) ** 2, p * p * c, device=dev, generator=g)
+        hh = H // p
+        img2 = torch.einsum("nhwpqc->nchpwq", z.reshape(3, hh, hh, p, p, c)).reshape(3, c, H, H).contiguous()
+        assert torch.equal(ops.unpatchify_bwd(img2, p).float(), z.reshape(-1, p * p * c).bfloat16().float())
+    pre = torch.randn(64, 384, device=dev, generator=g) * 2
+    d = torch.randn(64, 384, device=dev, generator=g)
+    pd = pre.double().requires_grad_(True)
+    F.silu(pd).backward(d.double())
+    assert rel_l2(ops.silu_bwd(d, pre), pd.grad) < 1e-6
+    yl = torch.tensor([3, 7, 3, 1000, 0, 3], device=dev)
+    dc = torch.randn(6, 384, device=dev, generator=g)
+    table = torch.zeros(1001, 384, device=dev)
+    ops.label_embed_bwd(dc, yl, table)
+    ref = torch.zeros(1001, 384, device=dev, dtype=torch.double).index_add_(0, yl, dc.double())
+    assert rel_l2(table, ref) < 1e-6
+
+
+@pytest.mark.parametrize("hd,H", [(64, 6), (72, 4)])
+@pytest.mark.parametrize("T", [64, 256, 100, 16])
+def test_attention_bwd(ops, dev, hd, H, T):
+    g = _g(7)
+    B = 2
+    D = H * hd
+    qkv = torch.randn(B * T, 3 * D, device=dev, generator=g).bfloat16()
+    dout = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+    lse = torch.empty(B, H, T, device=dev)
+    out = ops.attention(qkv, B, T, H, hd, lse=lse)
+    q = qkv.double().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+    o = F.scaled_dot_product_attention(q[0], q[1], q[2]).transpose(1, 2).reshape(B * T, D)
+    o.backward(dout.double())
+    ref = q.grad.permute(1, 3, 0, 2, 4).reshape(B * T, 3 * D)
+    got = ops.attention_bwd(qkv, out, dout, lse, B, T, H, hd)
+    for j, name in enumerate("qkv"):
+        assert rel_l2(got[:, j * D:(j + 1) * D].float(), ref[:, j * D:(j + 1) * D]) < 1.5e-2, name
+
+
+# ---------------------------------------------------------------------------- the whole step
+def _oracle_grads(model_cpu, name, x, t, y, dout=None, loss_fn=None):
+    from oracle import dit_oracle as O
+
+    cfg = O.config_for(name, input_size=x.shape[-1])
+    sd = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in model_cpu.state_dict(keep_vars=True).items()}
+    out = O.dit_forward(sd, cfg, x, t, y)
+    if loss_fn is None:
+        out.backward(dout)
+    else:
+        loss_fn(out).backward()
+    return out.detach(), {k: v.grad for k, v in sd.items() if v.requires_grad}
+
+
+@pytest.mark.parametrize("name,B", [("DiT-S/2", 4), ("DiT-S/8", 5), ("DiT-B/4", 8)])
+def test_model_gradients_against_oracle(dev, name, B):
+    """Every parameter's gradient of <dout, DiT(x, t, y)> in bf16 against the fp32 CPU oracle's autograd.
+    The reference's own bf16-autocast gradients sit ~1e-2 from its fp32 ones; bound per tensor 5e-2 and
+    2e-2 on the flattened whole."""
+    from util import build_product_model
+
+    m = build_product_model(name, input_size=32, num_classes=1000, precision="bf16")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    y = torch.randint(0, 1001, (B,), generator=g)
+    dout = torch.randn(B, 8, 32, 32, generator=g)
+    ref_out, ref = _oracle_grads(m, name, x, t, y, dout)
+    mc = m.cuda()  # eval mode: no label dropout, as in the oracle call
+    out = mc(x.cuda(), t.cuda(), y.cuda())
+    assert out.requires_grad
+    assert rel_l2(out, ref_out) < 1e-2
+    out.backward(dout.cuda())
+    num = den = 0.0
+    for k, p in mc.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        e = rel_l2(p.grad, ref[k])
+        assert e < 5e-2, (k, e)
+        num += float((p.grad.double().cpu() - ref[k].double()).pow(2).sum())
+        den += float(ref[k].double().pow(2).sum())
+    assert math.sqrt(num / den) < 2e-2
+    # a second step after zero_grad reuses the arena and gives the same gradients
+    first = {k: p.grad.clone() for k, p in mc.named_parameters() if p.grad is not None}
+    mc.zero_grad(set_to_none=True)
+    mc(x.cuda(), t.cuda(), y.cuda()).backward(dout.cuda())
+    for k, p in mc.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, first[k]) < 3e-3, k  # atomics reorder f32 sums that are then rounded to bf16 operands
+    # accumulating into live gradients (no zero_grad) doubles them
+    mc(x.cuda(), t.cuda(), y.cuda()).backward(dout.cuda())
+    for k, p in mc.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, 2 * first[k]) < 3e-3, k
+
+
+def test_training_losses_step_against_oracle(dev):
+    """create_diffusion('').training_losses(model, x0, t, dict(y=y))['loss'].mean().backward() — the
+    reference's training step (train_original.py:204-209) — against the oracle's loss and gradients."""
+    from fast_dit_b200 import create_diffusion
+    from oracle import dit_oracle as O
+    from oracle.diffusion_oracle import DiffusionOracle
+    from util import build_product_model
+
+    name, B = "DiT-S/2", 6
+    m = build_product_model(name, input_size=32, num_classes=1000, precision="bf16")
+    g = torch.Generator().manual_seed(12)
+    x0 = torch.randn(B, 4, 32, 32, generator=g)
+    noise = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.tensor([0, 1, 17, 500, 998, 999])
+    y = torch.randint(0, 1000, (B,), generator=g)
+    do = DiffusionOracle("")
+    x_t = do.q_sample(x0, t, noise)
+
+    def loss_fn(out):
+        return do.training_losses(out, x0, x_t, t, noise)["loss"].mean()
+
+    ref_out, ref = _oracle_grads(m, name, x_t, do.map_t(t), y, loss_fn=loss_fn)
+    ref_terms = do.training_losses(ref_out, x0, x_t, t, noise)
+    mc = m.cuda()
+    d = create_diffusion("")
+    terms = d.training_losses(mc, x0.cuda(), t.cuda(), dict(y=y.cuda()), noise=noise.cuda())
+    for k in ("loss", "mse", "vb"):
+        assert rel_l2(terms[k], ref_terms[k]) < 2e-2, k
+    terms["loss"].mean().backward()
+    num = den = 0.0
+    for k, p in mc.named_parameters():
+        if p.requires_grad:
+            num += float((p.grad.double().cpu() - ref[k].double()).pow(2).sum())
+            den += float(ref[k].double().pow(2).sum())
+    assert math.sqrt(num / den) < 3e-2
+
+
+def test_data_parallel_wrapper_single_rank(dev):
+    """parallel.DataParallel on one rank: buckets are issued final layer -> blocks L-1..0 -> embedders,
+    and the gradients equal the unwrapped model's."""
+    from fast_dit_b200.parallel import DataParallel
+    from util import build_product_model
+
+    m = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16").cuda()
+    g = _g(13)
+    x = torch.randn(4, 4, 32, 32, device=dev, generator=g)
+    t = torch.randint(0, 1000, (4,), device=dev, generator=g)
+    y = torch.randint(0, 1000, (4,), device=dev, generator=g)
+    dout = torch.randn(4, 8, 32, 32, device=dev, generator=g)
+    m(x, t, y).backward(dout)
+    plain = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    ddp = DataParallel(m)
+    ddp(x, t, y).backward(dout)
+    assert ddp.buckets_issued == ["final_layer"] + [f"blocks.{i}" for i in range(m.depth - 1, -1, -1)] + ["embed"]
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, plain[k]) < 3e-3, k
