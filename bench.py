@@ -37,6 +37,11 @@ WORKLOADS = {
     "c5": ("DiT-XL/2", 64, 8, "250"),
     "c1": ("DiT-S/2", 32, 4, "10"),
 }
+TRAIN_WORKLOADS = {
+    # name: (model, latent, images per GPU per step)   BASELINE.json configs[1] / configs[3]
+    "c2": ("DiT-B/4", 32, 256),
+    "c4": ("DiT-XL/2", 32, 32),
+}
 CFG_SCALE = 4.0
 
 
@@ -318,19 +323,138 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Training step (BASELINE.json configs[1]/[3]): t ~ U{0..999}; training_losses (q_sample,
+    model forward, MSE + VLB loss); backward; gradient all-reduce overlapped with backward when N > 1; fused
+    AdamW + EMA step.  One bench step = one optimizer step on `images` synthetic latents per GPU."""
+    import torch.distributed as dist
+
+    from fast_dit_b200 import DiT_models, create_diffusion, ops
+    from fast_dit_b200.optim import FusedAdamWEMA
+    from fast_dit_b200.parallel import DataParallel, init_from_env
+    from fast_dit_b200.utils import forward_flops_per_image, rerandomise_zero_params
+
+    rank, local, world = init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    name, lat, n = TRAIN_WORKLOADS[args.workload]
+    if args.images:
+        n = args.images
+    torch.manual_seed(0)
+    model = DiT_models[name](input_size=lat, num_classes=1000, precision="bf16")
+    rerandomise_zero_params(model)
+    model = model.to(dev).train()
+    opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999)
+    net = DataParallel(model) if world > 1 else model
+    diffusion = create_diffusion("")
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_h = torch.randn(n, 4, lat, lat, generator=g).pin_memory()
+    y_h = torch.randint(0, 1000, (n,), generator=g).pin_memory()
+    x_d, y_d = x_h.to(dev), y_h.to(dev)
+    loss_h = torch.empty(1).pin_memory()
+
+    def step(x, y):
+        t = torch.randint(0, diffusion.num_timesteps, (x.shape[0],), device=dev)
+        loss = diffusion.training_losses(net, x, t, dict(y=y))["loss"].mean()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def step_resident():
+        return step(x_d, y_d)
+
+    def step_e2e():
+        loss = step(x_h.to(dev, non_blocking=True), y_h.to(dev, non_blocking=True))
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.LAUNCHES
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = ops.LAUNCHES - l0
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        barrier()
+        return ms, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.finish()
+    ms_per_step = ms / args.steps
+    value = n * world / (ms_per_step / 1e3)
+    step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e /= args.steps
+    e2e = {"value": n * world / (ms_e2e / 1e3), "unit": "img/s", "h2d_bytes_per_step": x_h.numel() * 4 + y_h.numel() * 8,
+           "d2h_bytes_per_step": 4}
+    with ops.profile() as prof:
+        for _ in range(2):
+            step_resident()
+    summ = prof.summary()
+    ev_ms = sum(v[1] for v in summ.values()) / 2
+    g_n, g_ms, g_flops = summ["gemm_tc"]
+    tf_peak, hbm_peak, which = peaks()
+    achieved = g_flops / (g_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16: forward, data-gradient and weight-gradient GEMMs)",
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "peak_source": which,
+                "traffic": None, "launches_per_step": g_n // 2, "avg_launch_us": g_ms / g_n * 1e3,
+                "share_of_step": g_ms / 2 / ev_ms}
+    breakdown = {k: {"launches": v[0] // 2, "ms": v[1] / 2} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
+    flops_img = 3 * forward_flops_per_image(model)
+    line = {
+        "metric": f"{name} 256px training throughput (fwd + bwd + AdamW/EMA step)", "value": value, "unit": "img/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{name} {lat}x{lat}x4 latent training step, {n} images/GPU (global batch {n * world}), "
+                               "MSE + learned-sigma VLB loss, fused AdamW + EMA, random-init weights",
+                   "step_is": "one optimizer step", "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no flush needed",
+                   "parallelism": f"dp{world}, per-block gradient all-reduce (NCCL, f32, mean) overlapped with backward"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "mfu_bf16": {"value": value / world * flops_img / 1e12 / tf_peak, "denominator_tflops": tf_peak,
+                     "flops_per_image_G": flops_img / 1e9},
+        "steps_per_s": 1e3 / ms_per_step,
+        "kernel_breakdown_ms_per_step": breakdown,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + list(TRAIN_WORKLOADS))
     ap.add_argument("--images", type=int, default=0, help="kept images per GPU (default: the workload's)")
     ap.add_argument("--ref-images", type=int, default=2, help="kept images per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in TRAIN_WORKLOADS:
+        run_train(args)
     else:
         run_ours(args)
 

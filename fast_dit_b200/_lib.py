@@ -85,6 +85,7 @@ SIGNATURES = {
     "ditb200_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ditb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ditb200_final_layer": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
+    "ditb200_adamw_ema": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _vp]),
     "ditb200_cfg_combine": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "ditb200_p_sample_step": (_i, [C.POINTER(StepArgs), _vp]),
     "ditb200_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -32,6 +32,7 @@ SOURCES = [
     "gemm_tc.cu",
     "attention.cu",
     "backward.cu",
+    "optim.cu",
 ]
 
 NVCC_FLAGS = [

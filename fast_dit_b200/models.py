@@ -187,6 +187,9 @@ class DiT(nn.Module):
     def _shadows(self):
         """bf16 copies of the GEMM weights + the concatenated adaLN matrix, rebuilt whenever a
         parameter changes (optimizer step, load_state_dict, .to())."""
+        flat = getattr(self, "_flat", None)
+        if flat is not None:  # optim.FusedAdamWEMA owns the parameters and keeps the shadows in step
+            return flat.shadows()
         ada_w, ada_b = self._ada_params()
         gw = self._gemm_weights()
         key = (self.precision, ada_w[0].device, tuple(p._version for p in gw + ada_w + ada_b),
@@ -206,8 +209,9 @@ class DiT(nn.Module):
         self._shadow = sh
         return sh
 
-    def _apply(self, fn, *a, **k):  # .to()/.cuda() move parameters: drop stale shadows
+    def _apply(self, fn, *a, **k):  # .to()/.cuda() move parameters: drop stale shadows and arenas
         self._shadow = {}
+        self._flat = self._grad_arena = self._layout = None
         return super()._apply(fn, *a, **k)
 
     # ------------------------------------------------------------------------ forward

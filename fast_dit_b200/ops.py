@@ -375,3 +375,12 @@ def attention_bwd(qkv, out, dout, lse, B: int, T: int, H: int, hd: int):
     _call("attention_bwd", lib.ditb200_attention_bwd, _p(qkv), _p(out), _p(dout), _p(lse), _p(dsum), _p(dqkv),
           _DT[qkv.dtype], B, T, H, hd, _stream(), meta=10.0 * B * H * T * T * hd)
     return dqkv
+
+
+def adamw_ema(param, grad, exp_avg, exp_avg_sq, ema, shadow, *, lr, beta1, beta2, eps, weight_decay, step, ema_decay):
+    """One fused optimizer + EMA + bf16-shadow pass over flat arrays (csrc/optim.cu)."""
+    lib = _lib_for(param)
+    _chk_contig(param, grad, exp_avg, exp_avg_sq, ema, shadow)
+    _call("adamw_ema", lib.ditb200_adamw_ema, _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(ema), _p(shadow),
+          param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+          float(ema_decay), _stream())

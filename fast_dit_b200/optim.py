@@ -1,0 +1,122 @@
+"""Fused AdamW + EMA + bf16-shadow step over flat arenas.
+
+The reference's training loop (train.py:153-161,206-207; train_options/train_original.py:147,155,210-211)
+keeps `ema = deepcopy(model)`, runs `torch.optim.AdamW(lr=1e-4, weight_decay=0).step()` and then
+`update_ema(ema, model)`, a Python loop of mul_/add_ pairs — roughly 1200 small launches per step, and
+autocast re-casts every weight to bf16 in the next forward.  Here the parameters, gradients, Adam moments,
+EMA weights and bf16 shadows all share one layout (training.ArenaLayout) and `step()` is ONE kernel
+(csrc/optim.cu) that touches each byte once.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .training import GradArena, layout_for
+
+
+class FusedAdamWEMA:
+    """opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999)
+    loss.backward(); opt.step(); opt.zero_grad()
+
+    Construction moves the model's parameters into a flat f32 arena (each nn.Parameter becomes a view, so
+    state_dict()/load_state_dict()/DDP keep working) and attaches the arena to the model, whose forward
+    then reads its bf16 GEMM weights from the shadow arena this optimizer maintains."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=0.9999):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise L.Ditb200Error("FusedAdamWEMA needs the model on a CUDA device (there is no CPU path)")
+        self.model = model
+        self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        self.layout = lay = layout_for(model)
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(lay.total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p in self.params:
+                v = lay.view(self.flat, p)
+                v.copy_(p.data)
+                p.data = v
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.ema = self.flat.clone() if ema_decay is not None else None  # ema = deepcopy(model) (train.py:153)
+        self.shadow = torch.empty(lay.total, device=dev, dtype=torch.bfloat16) if model.precision == "bf16" else None
+        self.step_count = 0
+        self._views = None
+        self._versions = None
+        model._flat = self
+        model._shadow = {}
+        self.refresh()
+
+    # ------------------------------------------------------------------ what the model's forward reads
+    def _snapshot(self):
+        return tuple(p._version for p in self.params)
+
+    def refresh(self):
+        """Re-derive the bf16 shadows from the f32 master weights (after load_state_dict or any edit of
+        the parameters that did not go through step())."""
+        if self.shadow is not None:
+            ops.cast_bf16(self.flat, out=self.shadow)
+        self._versions = self._snapshot()
+
+    def shadows(self):
+        if self._versions != self._snapshot():
+            self.refresh()
+        if self._views is None:
+            m, lay = self.model, self.layout
+            src = self.shadow if self.shadow is not None else self.flat
+            lo, hi = lay.ranges["ada_w"]
+            blo, bhi = lay.ranges["ada_b"]
+            self._views = {
+                "key": "flat",
+                "w": [lay.view(src, w) for w in m._gemm_weights()],
+                "ada_w": src[lo:lo + lay.ada_rows * m.hidden_size].view(lay.ada_rows, m.hidden_size),
+                "ada_b": self.flat[blo:blo + lay.ada_rows],
+            }
+        return self._views
+
+    # ------------------------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self):
+        m = self.model
+        if getattr(m, "_flat", None) is not self:
+            raise L.Ditb200Error("the model's parameters were moved after FusedAdamWEMA was built; rebuild the optimizer")
+        arena = getattr(m, "_grad_arena", None)
+        if arena is None:
+            arena = GradArena(m)
+            m._grad_arena = arena
+        for p in self.params:  # gradients that did not land in the arena (torch DDP, accumulation, no backward)
+            if not arena.aliases(p):
+                if p.grad is None:
+                    arena.view(p).zero_()
+                else:
+                    arena.view(p).copy_(p.grad)
+        if self._versions != self._snapshot():
+            self.refresh()
+        self.step_count += 1
+        ops.adamw_ema(self.flat, arena.flat, self.exp_avg, self.exp_avg_sq, self.ema, self.shadow, lr=self.lr,
+                      beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
+                      step=self.step_count, ema_decay=self.ema_decay if self.ema is not None else 0.0)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    # --------------------------------------------------------------------------------- checkpoints
+    def ema_state_dict(self):
+        """state_dict of the EMA model (what train.py:233 saves under "ema"; download.py:26-29 loads it)."""
+        ids = {id(p): self.layout.view(self.ema, p) for p in self.params}
+        return {k: ids.get(id(v), v).detach().clone() for k, v in self.model.state_dict(keep_vars=True).items()}
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

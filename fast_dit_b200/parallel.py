@@ -137,11 +137,13 @@ class DataParallel(torch.nn.Module):
         self.buckets_issued.append(key)
         if self.world == 1:
             return
-        buf = arena.bucket(key)
-        if buf.is_cuda:  # NCCL averages in the collective
-            self._pending.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True), buf, True))
-        else:            # gloo (CPU tests of the host logic): sum, divide afterwards
-            self._pending.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), buf, False))
+        for buf in arena.bucket(key):
+            if buf.is_cuda:  # NCCL averages in the collective
+                work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+                self._pending.append((work, buf, True))
+            else:            # gloo (CPU tests of the host logic): sum, divide afterwards
+                work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                self._pending.append((work, buf, False))
 
     def forward(self, *args, **kwargs):
         self.buckets_issued = []

@@ -28,47 +28,92 @@ from . import _lib as L
 from . import ops
 
 
-# ------------------------------------------------------------------ gradient arena
-class GradArena:
-    """One flat f32 buffer holding every trainable parameter's gradient, in `parameters()` order.
+# ------------------------------------------------------------------ arenas
+class ArenaLayout:
+    """Where every trainable parameter lives in a flat array.  One layout is shared by the gradient arena,
+    and — when optim.FusedAdamWEMA owns the parameters — by the f32 master weights, the Adam moments, the
+    EMA weights and the bf16 weight shadows, so the optimizer is one pass over [0, total).
 
-    Buckets are contiguous slices: the embedders, each DiT block, the final layer — the order in which
-    backward completes them is final layer, blocks L-1..0, embedders."""
+    Order: embedders | per block {qkv, proj, fc1, fc2} weights+biases | final linear | every
+    adaLN_modulation weight (blocks 0..L-1, final layer) | every adaLN bias.  The adaLN weights are
+    contiguous and unpadded on purpose: that region IS the [(6L+2)·D, D] matrix of the batched adaLN GEMM.
+    Buckets (what a data-parallel step all-reduces as soon as it is complete): 'final_layer',
+    'blocks.i' for i = L-1..0, 'embed' (which also carries the small adaLN-bias region)."""
 
-    ALIGN = 64  # floats: every gradient starts on a 256-byte boundary (vector atomics / TMA-free stores)
+    ALIGN = 64  # floats: gradients start on 256-byte boundaries (vector atomics, 128-bit stores)
 
     def __init__(self, model):
-        self.offsets = {}
-        off = 0
-        self.bucket_ranges = {}
-        names = dict((id(p), n) for n, p in model.named_parameters())
+        ada_w, ada_b = model._ada_params()
+        ada_ids = {id(p) for p in ada_w + ada_b}
+        names = {id(p): n for n, p in model.named_parameters()}
+        groups = {"embed": [], "final_layer": []}
+        for i in range(model.depth):
+            groups[f"blocks.{i}"] = []
         for p in model.parameters():
-            if not p.requires_grad:
+            if not p.requires_grad or id(p) in ada_ids:
                 continue
             n = names[id(p)]
-            key = n.split(".")[0] + ("." + n.split(".")[1] if n.startswith("blocks.") else "")
-            if key in ("x_embedder", "t_embedder", "y_embedder"):
-                key = "embed"
-            start = off
-            self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
-            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-            lo, hi = self.bucket_ranges.get(key, (start, start))
-            self.bucket_ranges[key] = (min(lo, start), off)
+            head = n.split(".")[0]
+            key = "embed" if head in ("x_embedder", "t_embedder", "y_embedder") else \
+                  ".".join(n.split(".")[:2]) if head == "blocks" else head
+            groups[key].append(p)
+        self.offsets, self.ranges = {}, {}
+        off = 0
+
+        def place(plist, pad):
+            nonlocal off
+            lo = off
+            for p in plist:
+                self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
+                off += p.numel()
+                if pad:
+                    off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            return lo, off
+
+        for key in ["embed"] + [f"blocks.{i}" for i in range(model.depth)] + ["final_layer"]:
+            self.ranges[key] = place(groups[key], True)
+        assert all(p.numel() % 4 == 0 for p in ada_w + ada_b)
+        self.ranges["ada_w"] = place([p for p in ada_w if p.requires_grad], False)
+        self.ranges["ada_b"] = place([p for p in ada_b if p.requires_grad], False)
         self.total = off
-        dev = next(model.parameters()).device
-        self.flat = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        self.ada_rows = sum(p.shape[0] for p in ada_w)
+        self.buckets = {"embed": [self.ranges["embed"], self.ranges["ada_b"]]}
+        for i, p in enumerate(ada_w):
+            key = f"blocks.{i}" if i < model.depth else "final_layer"
+            o, n, _ = self.offsets[id(p)]
+            self.buckets[key] = [self.ranges[key], (o, o + n)]
+
+    def view(self, flat, p):
+        off, n, shape = self.offsets[id(p)]
+        return flat[off:off + n].view(shape)
+
+
+def layout_for(model) -> ArenaLayout:
+    lay = getattr(model, "_layout", None)
+    if lay is None:
+        lay = ArenaLayout(model)
+        model._layout = lay
+    return lay
+
+
+class GradArena:
+    """One flat f32 buffer holding every trainable parameter's gradient (layout: ArenaLayout)."""
+
+    def __init__(self, model):
+        self.layout = layout_for(model)
+        self.flat = torch.zeros(self.layout.total, device=next(model.parameters()).device, dtype=torch.float32)
 
     def view(self, p):
-        off, n, shape = self.offsets[id(p)]
-        return self.flat[off:off + n].view(shape)
+        return self.layout.view(self.flat, p)
 
     def bucket(self, key):
-        lo, hi = self.bucket_ranges[key]
-        return self.flat[lo:hi]
+        """The contiguous slices that make up one data-parallel bucket."""
+        return [self.flat[lo:hi] for lo, hi in self.layout.buckets[key]]
 
     def aliases(self, p):
         g = p.grad
-        return g is not None and g.data_ptr() == self.flat.data_ptr() + 4 * self.offsets[id(p)][0]
+        return g is not None and g.data_ptr() == self.flat.data_ptr() + 4 * self.layout.offsets[id(p)][0]
 
 
 def _arena_for(model):
@@ -80,7 +125,10 @@ def _arena_for(model):
         ar = GradArena(model)
         model._grad_arena = ar
         return ar
-    if getattr(model, "_grad_sync", None) is None and any(ar.aliases(p) for p in model.parameters() if p.requires_grad):
+    if any(ar.aliases(p) for p in model.parameters() if p.requires_grad):
+        if getattr(model, "_grad_sync", None) is not None:
+            raise L.Ditb200Error("DataParallel needs zero_grad(set_to_none=True) between steps: gradient "
+                                 "accumulation across backward calls is not supported under data parallelism")
         return GradArena(model)
     return ar
 

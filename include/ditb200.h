@@ -231,6 +231,17 @@ int ditb200_final_layer(const float* x, const float* shift, const float* scale, 
                         const float* w, const float* bias, float* out, int B, int T, int D, int p,
                         int Cout, float eps, int round_bf16, void* stream);
 
+/* ------------------------------------------------------------- optimizer */
+
+/* One fused pass over flat f32 arrays of n elements (n % 4 == 0): torch.optim.AdamW's update
+ * (decoupled weight decay, bias correction with `step` >= 1), the EMA update
+ * ema = ema_decay*ema + (1-ema_decay)*param (train.py:41-51; ema may be NULL) and the bf16 copy of the
+ * updated parameters that the next forward's tensor-core GEMMs read (shadow_bf16 may be NULL).
+ * Replaces opt.step() + update_ema() (train.py:161,206-207; train_options/train_original.py:210-211). */
+int ditb200_adamw_ema(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema,
+                      void* shadow_bf16, size_t n, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int step, float ema_decay, void* stream);
+
 /* ------------------------------------------------------------- diffusion */
 
 /* Classifier-free-guidance combine on the model output.

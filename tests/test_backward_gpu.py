@@ -299,3 +299,55 @@ def test_data_parallel_wrapper_single_rank(dev):
     for k, p in m.named_parameters():
         if p.grad is not None:
             assert rel_l2(p.grad, plain[k]) < 3e-3, k
+
+
+def test_fused_adamw_ema_matches_torch(dev):
+    """optim.FusedAdamWEMA against torch.optim.AdamW + the reference's update_ema loop (train.py:41-51,161)
+    fed the same gradients for three steps; the bf16 shadows the next forward reads track the weights."""
+    import copy
+
+    from fast_dit_b200.optim import FusedAdamWEMA
+    from util import build_product_model
+
+    m = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16").cuda().train()
+    ref = copy.deepcopy(m)
+    ema_ref = copy.deepcopy(m)
+    opt = FusedAdamWEMA(m, lr=1e-3, weight_decay=0.01, ema_decay=0.99)
+    opt_ref = torch.optim.AdamW([p for p in ref.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.01)
+    g = _g(21)
+    for step in range(3):
+        x = torch.randn(4, 4, 32, 32, device=dev, generator=g)
+        t = torch.randint(0, 1000, (4,), device=dev, generator=g)
+        y = torch.randint(0, 1000, (4,), device=dev, generator=g)
+        dout = torch.randn(4, 8, 32, 32, device=dev, generator=g)
+        torch.manual_seed(100 + step)  # label dropout draw
+        m(x, t, y).backward(dout)
+        for (k, p), q in zip(m.named_parameters(), ref.parameters()):
+            q.grad = None if p.grad is None else p.grad.clone()
+        opt.step()
+        opt.zero_grad()
+        opt_ref.step()
+        with torch.no_grad():
+            for e, q in zip(ema_ref.parameters(), ref.parameters()):
+                if q.requires_grad:
+                    e.mul_(0.99).add_(q.data, alpha=0.01)
+        for (k, p), q in zip(m.named_parameters(), ref.parameters()):
+            assert rel_l2(p, q) < 1e-6, (step, k)
+    ema_sd = opt.ema_state_dict()
+    for k, e in ema_ref.state_dict().items():
+        assert rel_l2(ema_sd[k], e) < 1e-6, k
+    sh = m._shadows()
+    assert torch.equal(sh["w"][0], m.blocks[0].attn.qkv.weight.detach().bfloat16())
+    D = m.hidden_size
+    assert torch.equal(sh["ada_w"][6 * D:12 * D], m.blocks[1].adaLN_modulation[1].weight.detach().bfloat16())
+    assert torch.equal(sh["ada_b"][-2 * D:], m.final_layer.adaLN_modulation[1].bias.detach())
+    # the forward after the step uses the updated weights (and load_state_dict refreshes the shadows)
+    m.eval()
+    with torch.no_grad():
+        a = m(x, t, y)
+        ref.eval()
+        b = ref(x, t, y)
+        assert rel_l2(a, b) < 1e-3
+        m.load_state_dict(ema_sd)
+        ema_ref.eval()
+        assert rel_l2(m(x, t, y), ema_ref(x, t, y)) < 1e-3
