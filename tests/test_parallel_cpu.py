@@ -80,3 +80,73 @@ def test_two_rank_gloo_sharding():
         assert p.exitcode == 0
     ok, distinct, tmax, total = q.get(timeout=10)
     assert ok and distinct and tmax == 15.0 and total == 24
+
+
+# ------------------------------------------------------------------ training: gradient buckets
+def test_arena_layout_buckets_cover_every_parameter_once():
+    from fast_dit_b200.models import DiT_models
+    from fast_dit_b200.training import ArenaLayout
+
+    m = DiT_models["DiT-S/4"](input_size=32)
+    lay = ArenaLayout(m)
+    covered = torch.zeros(lay.total, dtype=torch.int32)
+    for key, slices in lay.buckets.items():
+        for lo, hi in slices:
+            covered[lo:hi] += 1
+    assert int(covered.max()) == 1, "buckets overlap"
+    for p in m.parameters():
+        if p.requires_grad:
+            off, n, shape = lay.offsets[id(p)]
+            assert off % 4 == 0 and shape == tuple(p.shape)
+            assert int(covered[off:off + n].min()) == 1, "a parameter is outside every bucket"
+    # the adaLN weight region is exactly the batched [(6L+2) D, D] matrix, blocks first, final layer last
+    lo, hi = lay.ranges["ada_w"]
+    D = m.hidden_size
+    assert lay.ada_rows == (6 * m.depth + 2) * D and hi - lo >= lay.ada_rows * D
+    assert lay.offsets[id(m.blocks[3].adaLN_modulation[1].weight)][0] == lo + 3 * 6 * D * D
+    assert lay.offsets[id(m.final_layer.adaLN_modulation[1].weight)][0] == lo + m.depth * 6 * D * D
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fast_dit_b200.models import DiT_models
+    from fast_dit_b200.parallel import DataParallel, init_from_env
+    from fast_dit_b200.training import GradArena
+
+    init_from_env("gloo")
+    torch.manual_seed(rank)  # different initial weights per rank: the wrapper must broadcast rank 0's
+    m = DiT_models["DiT-S/8"](input_size=32)
+    ddp = DataParallel(m)
+    w0 = m.blocks[0].attn.qkv.weight.detach().clone()
+    ws = [torch.empty_like(w0) for _ in range(world)]
+    dist.all_gather(ws, w0)
+    same_weights = torch.equal(ws[0], ws[1])
+    # emulate a backward: rank r's gradient arena holds (r + 1) everywhere; buckets are reduced in the order
+    # backward completes them; afterwards every gradient must be the mean over ranks
+    arena = GradArena(m)
+    arena.flat.fill_(float(rank + 1))
+    order = ["final_layer"] + [f"blocks.{i}" for i in range(m.depth - 1, -1, -1)] + ["embed"]
+    for key in order:
+        m._grad_sync(key, arena)
+    m._grad_sync(None, arena)
+    mean = sum(range(1, world + 1)) / world
+    ok = all(bool((arena.view(p) == mean).all()) for p in m.parameters() if p.requires_grad)
+    dist.barrier()
+    if rank == 0:
+        q.put((same_weights, ok, ddp.buckets_issued == order))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_buckets():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    same_weights, ok, order_ok = q.get(timeout=10)
+    assert same_weights and ok and order_ok
