@@ -24,6 +24,8 @@
 //               back.  Runs concurrently with the next tile's main loop.
 // Work units are (tile, k-split); tiles are visited n-fastest so the CTAs running at the same time
 // share A row-panels in L2.  With split_k > 1 partial tiles are combined with f32 vector atomics.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ditb200 {
@@ -33,7 +35,8 @@ constexpr int kBK = 64;        // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kEpiStageBytes = 32 * 128;                 // per epilogue warp: 32 rows x 32 f32 transpose buffer
+constexpr int kSmemBudget = 232448 - 1024 - 256 - kEpiWarps * kEpiStageBytes;  // what is left for the TMA ring
 constexpr int kMnChunkBytes = 64 * kBK * 2;  // one {64 MN x 64 k} TMA box of an MN-major operand
 
 struct EpiParams {
@@ -56,8 +59,10 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "UMMA N / epilogue column split");
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "UMMA N / epilogue column split (32-column chunks per half)");
+  // epilogue column split between the two warps of a lane quarter: [0, kHalf0) and [kHalf0, BN)
+  static constexpr int kHalf0 = BN / 2;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(kABytes % 1024 == 0 && kBBytes % 1024 == 0, "swizzle-128B tiles need 1024-B alignment");
 };
@@ -67,16 +72,184 @@ __device__ __forceinline__ float dgelu_tanh_f(float u) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   const float u2 = u * u;
   const float z = k0 * (u + k1 * u2 * u);
-  const float e = __expf(2.0f * z);
-  const float t = 1.0f - __fdividef(2.0f, e + 1.0f);  // tanh(z)
+  const float t = tanh_approx(z);
   return 0.5f * (1.0f + t) + 0.5f * u * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * u2);
 }
+
+// ------------------------------------------------------------------------------ epilogue
+// One epilogue warp owns 32 accumulator rows (its TMEM lane quarter) x NCH 32-column chunks of the tile.
+// tcgen05.ld hands every thread one ROW (32 consecutive columns); storing that way would touch 32 different
+// 128-byte lines per instruction.  The warp therefore transposes each chunk through its private 4 KB staging
+// buffer (16-byte slots XOR-swizzled by row: conflict-free in both directions) and does all global traffic with
+// lane = 4 consecutive columns: 8 lanes cover one 128-byte row segment, one instruction covers 4 full rows.
+// EPI / OUT / AUX are compile-time (-1 = decide at run time): the kernel dispatches once per tile to a
+// straight-line instantiation instead of re-deciding the epilogue flavour for every row.
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC = 2 };
+
+template <int EPI, int OUT, int AUX, int NCH>
+__device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t taddr0, uint8_t* stg, const int lane,
+                                         const int row0, const int colw, const int nch, const int M, const int N,
+                                         const bool add_bias) {
+  const int epi = EPI >= 0 ? EPI : ep.epilogue;
+  const int omode = OUT >= 0 ? OUT : (ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32));
+  const bool aux = AUX >= 0 ? (AUX != 0) : (ep.aux_out != nullptr);
+  const int sub = lane >> 3, grp = lane & 7;
+  const int rows_valid = M - row0;  // rows [0, rows_valid) of this warp's 32 exist (may be <= 0 or >= 32)
+  uint8_t* my_row = stg + lane * 128;
+  const int swz_w = lane & 7;
+  // adaLN gate: one [N] vector per image.  Fast path: all 32 rows belong to the same image.
+  const float* gate_base = nullptr;
+  bool gate_uniform = true;
+  if (epi == DITB200_EPI_BIAS_GATE_RESID) {
+    const int last = min(row0 + 31, M - 1);
+    const int g_lo = row0 / ep.rows_per_gate, g_hi = max(last, row0) / ep.rows_per_gate;
+    gate_uniform = g_lo == g_hi;
+    gate_base = ep.gate + (size_t)(rows_valid > 0 ? g_lo : 0) * ep.gate_stride;
+  }
+  float4 r4[8];  // residual values of the chunk, requested before the accumulators are waited for (GATE_RESID only)
+  auto load_resid = [&](int c, float4 (&dst)[8]) {
+    const int col = colw + c * 32 + grp * 4;
+    const float* rp = ep.resid + (size_t)row0 * N + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + sub;
+      if (col < N && r < rows_valid) dst[i] = *reinterpret_cast<const float4*>(rp + (size_t)r * N);
+    }
+  };
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    if (c >= nch || colw + c * 32 >= N) break;  // warp-uniform: narrow last tile column / columns past the matrix
+    uint32_t v[32];
+    tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+    if (epi == DITB200_EPI_BIAS_GATE_RESID) load_resid(c, r4);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<uint4*>(my_row + ((g ^ swz_w) << 4)) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    __syncwarp();
+    const int col = colw + c * 32 + grp * 4;
+    if (col < N) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (add_bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (epi == DITB200_EPI_BIAS_GATE_RESID && gate_uniform) g4 = __ldg(reinterpret_cast<const float4*>(gate_base + col));
+      const size_t off0 = (size_t)row0 * N + col;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub;
+        if (r < rows_valid) {
+          float4 f = *reinterpret_cast<const float4*>(stg + r * 128 + ((grp ^ (r & 7)) << 4));
+          f.x += b4.x, f.y += b4.y, f.z += b4.z, f.w += b4.w;
+          const size_t off = off0 + (size_t)r * N;
+          if (aux) {  // the pre-activation / un-gated branch value, kept for backward
+            uint2 pk;
+            pk.x = pack_bf16x2(f.x, f.y), pk.y = pack_bf16x2(f.z, f.w);
+            *reinterpret_cast<uint2*>(ep.aux_out + off) = pk;
+          }
+          if (epi == DITB200_EPI_BIAS_GELU) {
+            f.x = gelu_tanh_fast(f.x), f.y = gelu_tanh_fast(f.y), f.z = gelu_tanh_fast(f.z), f.w = gelu_tanh_fast(f.w);
+          } else if (epi == DITB200_EPI_BIAS_SILU) {
+            f.x = silu_f(f.x), f.y = silu_f(f.y), f.z = silu_f(f.z), f.w = silu_f(f.w);
+          } else if (epi == DITB200_EPI_BIAS_GATE_RESID) {
+            if (!gate_uniform)
+              g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((row0 + r) / ep.rows_per_gate) * ep.gate_stride + col));
+            const float4 rr = r4[i];
+            f.x = fmaf(g4.x, f.x, rr.x), f.y = fmaf(g4.y, f.y, rr.y), f.z = fmaf(g4.z, f.z, rr.z), f.w = fmaf(g4.w, f.w, rr.w);
+          } else if (epi == DITB200_EPI_MUL_DGELU) {
+            const uint2 pk = *reinterpret_cast<const uint2*>(ep.aux_in + off);
+            const float2 u0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 u1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            f.x *= dgelu_tanh_f(u0.x), f.y *= dgelu_tanh_f(u0.y), f.z *= dgelu_tanh_f(u1.x), f.w *= dgelu_tanh_f(u1.y);
+          }
+          if (omode == OUT_BF16) {
+            uint2 pk;
+            pk.x = pack_bf16x2(f.x, f.y), pk.y = pack_bf16x2(f.z, f.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + off) = pk;
+          } else if (omode == OUT_ATOMIC) {
+            atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off), f);
+          } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + off) = f;
+          }
+        }
+      }
+    }
+    __syncwarp();  // the staging buffer is rewritten by the next chunk
+  }
+}
+
+// ------------------------------------------------------------------------------ tile schedule
+// Static schedule shared by the three warp roles of a CTA (pair).  Work units are output tiles (x k-splits).
+// When N is not a multiple of BN the last tile column is NARROW: its tcgen05.mma runs with N = part_cols
+// (the instruction descriptor is a run-time value) instead of multiplying zero-filled rows, and the schedule
+// hands those cheap tiles to the CTAs that received one full tile less (longest-processing-time order):
+//   phase 0  full tiles f = p, p+P, ...            (n-fastest, so concurrent CTAs share A row panels in L2)
+//   phase 1  CTAs p >= r (r = F mod P, the "light" ones) take q narrow tiles each
+//   phase 2  whatever narrow tiles are left, round-robin
+// With split_k > 1 the plain round-robin over (tile, split) units is kept.
+struct TileSched {
+  int P, p;                 // CTAs (pairs) in the grid, this CTA's index
+  int n_full, part_cols;    // full tile columns, width of the narrow last column (0 = none)
+  int F, H, r, q;           // full tiles, narrow tiles, light-CTA threshold, narrow tiles per light CTA
+  int split_k, n_tiles, num_units;
+  int phase, cur, end_a;
+
+  __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair) {
+    P = pairs, p = pair, split_k = split;
+    const int m_tiles = (M + tile_m - 1) / tile_m;
+    n_tiles = (N + bn - 1) / bn;
+    num_units = m_tiles * n_tiles * split_k;
+    part_cols = part;
+    n_full = part ? n_tiles - 1 : n_tiles;
+    F = m_tiles * n_full, H = part ? m_tiles : 0;
+    r = F % P;
+    q = part ? max(1, bn / part) : 1;
+    phase = 0, cur = p, end_a = 0;
+  }
+  // next unit of this CTA: tile coordinates, tile width in columns, k-split index
+  __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+    if (split_k > 1 || part_cols == 0) {  // plain round-robin
+      if (cur >= num_units) return false;
+      const int tile = cur / split_k;
+      split = cur - tile * split_k;
+      m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      ncols = (part_cols && n_blk == n_tiles - 1) ? part_cols : bn;
+      cur += P;
+      return true;
+    }
+    split = 0;
+    if (phase == 0) {
+      if (cur < F) {
+        m_blk = cur / n_full, n_blk = cur - m_blk * n_full, ncols = bn;
+        cur += P;
+        return true;
+      }
+      phase = 1;
+      cur = (p >= r) ? (p - r) * q : H;
+      end_a = min(H, cur + q);
+    }
+    if (phase == 1) {
+      if (cur < end_a) {
+        m_blk = cur, n_blk = n_full, ncols = part_cols;
+        ++cur;
+        return true;
+      }
+      phase = 2;
+      cur = (P - r) * q + p;
+    }
+    if (cur < H) {
+      m_blk = cur, n_blk = n_full, ncols = part_cols;
+      cur += P;
+      return true;
+    }
+    return false;
+  }
+};
 
 template <int kCG, int BN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
-               const int split_k) {
+               const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
+               const int split_k, const int part_cols) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +257,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * kEpiStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -115,13 +289,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tile_m = kBM * kCG;
-  const int m_tiles = (M + tile_m - 1) / tile_m;
-  const int n_tiles = (N + BN - 1) / BN;
   const int k_blocks = (K + kBK - 1) / kBK;
   const int kb_per = (k_blocks + split_k - 1) / split_k;
-  const int num_units = m_tiles * n_tiles * split_k;  // work units = (tile, k-split)
-  const int cta_unit = blockIdx.x / kCG;              // CTA (pair) index
-  const int num_ctas = gridDim.x / kCG;
+  TileSched sched;
+  sched.init(M, N, tile_m, BN, part_cols, split_k, (int)gridDim.x / kCG, (int)blockIdx.x / kCG);
+  int m_blk, n_blk, ncols, split;
 
   // Producer and MMA roles run warp-uniform loops (every lane waits on the barriers) and elect one
   // lane only around the asynchronous issues.  Keeping the control flow uniform lets the compiler
@@ -132,11 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = cta_unit; u < num_units; u += num_ctas) {
-      const int tile = u / split_k, split = u - tile * split_k;
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+    while (sched.next(BN, m_blk, n_blk, ncols, split)) {
       const int row_a = m_blk * tile_m + (int)cta_rank * kBM;
-      const int row_b = n_blk * BN + (int)cta_rank * Cfg::kBRows;
+      const int row_b = n_blk * BN + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
@@ -176,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
     if (leader) {
-      const uint32_t idesc = umma_idesc_bf16(kBM * kCG, BN) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+      const uint32_t idesc0 = umma_idesc_bf16(kBM * kCG, 0) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
       // descriptor hi word: SBO 1024 B (next 8-row group) | version 1 | SWIZZLE_128B
       constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       // descriptor lo word: start address >> 4 | LBO << 16.  K-major: LBO unused, +32 B per 16-k step.
@@ -188,8 +358,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int u = cta_unit; u < num_units; u += num_ctas, ++iter) {
-        const int split = u % split_k;
+      for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
+        const uint32_t idesc = idesc0 | ((uint32_t)(ncols >> 3) << 17);
         const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
@@ -220,120 +390,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ========================================================================= epilogue
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
-    const int row_in_tile = quarter * 32 + lane;
-    constexpr int kChunks = BN / 64;      // 32-column chunks per warp
+    uint8_t* stg = smem_epi + (warp - 2) * kEpiStageBytes;
     int iter = 0;
-    for (int u = cta_unit; u < num_units; u += num_ctas, ++iter) {
-      const int tile = u / split_k, split = u - tile * split_k;
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+    for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int row = m_blk * tile_m + (int)cta_rank * kBM + row_in_tile;
-      const int col0 = n_blk * BN + half * (BN / 2);
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const bool row_ok = row < M;
-      const bool add_bias = ep.bias != nullptr && split == 0;
-      const float* gate_row = nullptr;
-      if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID && row_ok)
-        gate_row = ep.gate + (size_t)(row / ep.rows_per_gate) * ep.gate_stride;
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)(acc * BN + half * (BN / 2) + c * 32);
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
-        const int col = col0 + c * 32;
-        if (!row_ok || col >= N) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (add_bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col + j < N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + j));
-              f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
-            }
-          }
-        }
-        if (ep.aux_out != nullptr) {  // the pre-activation / un-gated branch value, kept for backward
-          __nv_bfloat16* arow = ep.aux_out + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col + j < N) {
-              uint4 pk;
-              pk.x = pack_bf16x2(f[j], f[j + 1]), pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              pk.z = pack_bf16x2(f[j + 4], f[j + 5]), pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(arow + j) = pk;
-            }
-          }
-        }
-        if (ep.epilogue == DITB200_EPI_BIAS_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
-        } else if (ep.epilogue == DITB200_EPI_BIAS_SILU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-        } else if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID) {
-          const float* rrow = ep.resid + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col + j < N) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gate_row + col + j));
-              const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-              f[j] = fmaf(g4.x, f[j], r4.x);
-              f[j + 1] = fmaf(g4.y, f[j + 1], r4.y);
-              f[j + 2] = fmaf(g4.z, f[j + 2], r4.z);
-              f[j + 3] = fmaf(g4.w, f[j + 3], r4.w);
-            }
-          }
-        } else if (ep.epilogue == DITB200_EPI_MUL_DGELU) {
-          const __nv_bfloat16* urow = ep.aux_in + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col + j < N) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(urow + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 uu = __bfloat1622float2(h2[q]);
-                f[j + 2 * q] *= dgelu_tanh_f(uu.x);
-                f[j + 2 * q + 1] *= dgelu_tanh_f(uu.y);
-              }
-            }
-          }
-        }
-        if (ep.out_bf16) {
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col + j < N) {
-              uint4 pk;
-              pk.x = pack_bf16x2(f[j], f[j + 1]);
-              pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-              pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-              pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
-              *reinterpret_cast<uint4*>(orow + j) = pk;
-            }
-          }
-        } else if (ep.atomic) {
-          float* orow = reinterpret_cast<float*>(ep.out) + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col + j < N)
-              atomicAdd(reinterpret_cast<float4*>(orow + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
-          }
-        } else {
-          float* orow = reinterpret_cast<float*>(ep.out) + (size_t)row * N + col;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col + j < N)
-              *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          }
+      const int row0 = m_blk * tile_m + (int)cta_rank * kBM + quarter * 32;  // first row of this warp's lane quarter
+      if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID) {
+        // The residual tile does not depend on the MMAs: pull this warp's 32 x (ncols/2) block towards L2
+        // while the accumulators are still being produced, so the epilogue loads below do not pay HBM latency.
+        const int chunks_ = (ncols + 31) >> 5, c0_ = (chunks_ + 1) >> 1;
+        const int pc0 = n_blk * BN + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
+        if (row0 + lane < M) {
+          const float* rp = ep.resid + (size_t)(row0 + lane) * N + pc0;
+          for (int c = 0; c < pn; ++c)
+            if (pc0 + c * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c * 32));
         }
       }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const bool add_bias = ep.bias != nullptr && split == 0;
+      // the tile's 32-column chunks are split between the two warps of the lane quarter (narrow tiles too)
+      const int chunks = (ncols + 31) >> 5, chunks0 = (chunks + 1) >> 1;
+      const int col_off = half ? chunks0 * 32 : 0;  // first tile column of this warp
+      const int nch = half ? chunks - chunks0 : chunks0;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_off);
+      const int colw = n_blk * BN + col_off;
+      constexpr int NCH = BN / 64;
+#define EPI_CASE(E, O, A) epi_tile<E, O, A, NCH>(ep, taddr0, stg, lane, row0, colw, nch, M, N, add_bias)
+      const bool has_aux = ep.aux_out != nullptr;
+      const int omode = ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32);
+      if (ep.epilogue == DITB200_EPI_BIAS && !has_aux) {
+        if (omode == OUT_BF16) EPI_CASE(DITB200_EPI_BIAS, OUT_BF16, 0);
+        else if (omode == OUT_F32) EPI_CASE(DITB200_EPI_BIAS, OUT_F32, 0);
+        else EPI_CASE(DITB200_EPI_BIAS, OUT_ATOMIC, 0);
+      } else if (ep.epilogue == DITB200_EPI_BIAS_GELU && omode == OUT_BF16) {
+        if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GELU, OUT_BF16, 1); else EPI_CASE(DITB200_EPI_BIAS_GELU, OUT_BF16, 0);
+      } else if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID && omode == OUT_F32) {
+        if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 1); else EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 0);
+      } else if (ep.epilogue == DITB200_EPI_MUL_DGELU && omode == OUT_BF16 && !has_aux) {
+        EPI_CASE(DITB200_EPI_MUL_DGELU, OUT_BF16, 0);
+      } else {
+        EPI_CASE(-1, -1, -1);  // rare combinations: everything decided at run time
+      }
+#undef EPI_CASE
       // all tcgen05.ld of this stage are complete (wait::ld above): give the stage back
       tcgen05_fence_before();
       __syncwarp();
@@ -370,6 +470,19 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
     return DITB200_EINVAL;
   }
   return 0;
+}
+
+// Width of the narrow last tile column (0 = N is a multiple of bn, or narrowing is not possible).  tcgen05.mma
+// needs N % 16 == 0; an MN-major B operand is fetched in 64-column boxes per CTA.
+static int narrow_cols(int N, int bn, int cg, int trans_w) {
+  const int rem = N % bn;
+  if (rem == 0) return 0;
+  static const bool off = getenv("DITB200_NO_NARROW") != nullptr;  // measurement switch
+  if (off) return 0;
+  const int np = (rem + 15) / 16 * 16;
+  if (np >= bn) return 0;
+  if (trans_w && (np / cg) % 64 != 0) return 0;
+  return np;
 }
 
 template <int kCG, int BN>
@@ -419,21 +532,60 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN>, ta, tb, ep, a->M, a->N, a->K,
-                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k);
+                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k,
+                                     narrow_cols(a->N, BN, kCG, a->trans_w));
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
 }
 
-// Tile choice, from measurements on B200 (profiles/r01_gemm_notes.md): the widest tile wins for every
-// DiT shape because the per-k-block issue/barrier cost is amortised over twice the MMA work, and the
-// CTA pair halves each SM's B traffic.  Narrow tiles only when N itself is narrow; single CTAs when M
-// fits one 128-row tile (adaLN, M = batch).  An MN-major B operand is fetched in 64-row boxes, so its
-// per-CTA share must be a multiple of 64 (no 192-wide pair tile).
-static void choose_tile(int M, int N, int trans_w, int* cg_out, int* bn_out) {
-  *cg_out = (M > kBM) ? 2 : 1;
-  int bn = (N > 192) ? 256 : (N > 128) ? 192 : 128;
-  if (trans_w && bn == 192) bn = 256;
-  *bn_out = bn;
+// Tile choice.  Measured on B200 (profiles/r01_gemm_notes.md): per flop the 256-wide pair tile is the most
+// efficient (the 12 TB/s L2->SM fabric, not the tensor pipe, bounds the main loop, and arithmetic intensity
+// grows with the tile), 192 is within a few per cent, 128 costs ~30 %.  What decides between them for a given
+// shape is the length of the schedule: the chooser replays TileSched on the host for every legal width and takes
+// the smallest (max columns assigned to any CTA) / efficiency.
+static double sched_cost(int M, int N, int cg, int bn, int trans_w, int split_k) {
+  const int tile_m = kBM * cg;
+  const int m_tiles = (M + tile_m - 1) / tile_m;
+  const int part = narrow_cols(N, bn, cg, trans_w);
+  const int n_tiles = (N + bn - 1) / bn;
+  const double eff = bn >= 256 ? 1.0 : (bn >= 192 ? 0.97 : 0.72);
+  int P = num_sms() / cg;
+  const int units = m_tiles * n_tiles * split_k;
+  if (P > units) P = units;
+  if (split_k > 1 || part == 0) {
+    const int per = (units + P - 1) / P;
+    return (double)per * bn / split_k / eff;
+  }
+  // replay of TileSched (split_k == 1): columns assigned to every CTA
+  const int F = m_tiles * (n_tiles - 1), H = m_tiles;
+  const int r = F % P, q = bn / part > 1 ? bn / part : 1;
+  int load[160];
+  for (int p = 0; p < P; ++p) load[p] = (F / P + (p < r ? 1 : 0)) * bn;
+  int j = 0;
+  for (int p = r; p < P && j < H; ++p)
+    for (int t = 0; t < q && j < H; ++t, ++j) load[p] += part;
+  for (int p = 0; j < H; ++j, p = (p + 1 == P ? 0 : p + 1)) load[p] += part;
+  int mx = 0;
+  for (int p = 0; p < P; ++p) mx = load[p] > mx ? load[p] : mx;
+  return (double)mx / eff;
+}
+
+static void choose_tile(int M, int N, int trans_w, int split_k, int* cg_out, int* bn_out) {
+  const int cg = (M > kBM) ? 2 : 1;
+  *cg_out = cg;
+  const int cand[3] = {256, 192, 128};
+  double best = 1e30;
+  int best_bn = 128;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (trans_w && (bn / cg) % 64 != 0) continue;   // MN-major B: 64-column boxes per CTA
+    if (bn > 128 && N <= bn - 64) continue;          // a tile wider than the matrix buys nothing
+    double c = sched_cost(M, N, cg, bn, trans_w, split_k);
+    // measured: with few tile columns an exact 192-wide cover beats 256 + a narrow column by 3-8 % (N = 1152)
+    if (bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048) c *= 0.8;
+    if (c < best) best = c, best_bn = bn;
+  }
+  *bn_out = best_bn;
 }
 
 int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
@@ -469,7 +621,7 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   int cg = a->cta_group, bn = a->tile_n;
   if (cg == 0 || bn == 0) {
     int acg, abn;
-    choose_tile(a->M, a->N, a->trans_w, &acg, &abn);
+    choose_tile(a->M, a->N, a->trans_w, split_k, &acg, &abn);
     if (cg == 0) cg = acg;
     if (bn == 0) bn = abn;
   }
