@@ -31,6 +31,7 @@ SOURCES = [
     "gemm_simt.cu",
     "gemm_tc.cu",
     "attention.cu",
+    "attention_tc.cu",
     "backward.cu",
     "optim.cu",
 ]

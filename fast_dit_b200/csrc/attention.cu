@@ -6,6 +6,8 @@
 //                 accumulation, online softmax in f32 (exp2), K/V double-buffered with cp.async.
 //                 hd = 72 (DiT-XL) is zero-padded to 80 in shared memory only.
 //   f32 engine  : CUDA-core kernel for the fp32 check mode.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ditb200 {
@@ -643,6 +645,12 @@ static int launch_attn_bf16(const void* qkv, void* out, float* lse, int B, int T
   return 0;
 }
 
+namespace ditb200 {
+// attention_tc.cu: tcgen05 / TMEM forward for T in {128, 256}, head dim 64..80
+bool attn_fwd_tc_supported(int T, int hd);
+int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+}  // namespace ditb200
+
 extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
                                      int hd, void* stream) {
   DITB_REQUIRE(qkv && out, DITB200_EINVAL, "attention_fwd: null pointer");
@@ -651,6 +659,8 @@ extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DITB200_BF16) {
     DITB_REQUIRE(aligned16(qkv) && aligned16(out), DITB200_EALIGN, "attention_fwd: misaligned pointer");
+    static const bool legacy = getenv("DITB200_ATTN_MMA_SYNC") != nullptr;  // measurement switch
+    if (!legacy && attn_fwd_tc_supported(T, hd)) return launch_attn_fwd_tc(qkv, out, lse, B, T, H, hd, st);
     if (hd == 64) return launch_attn_bf16<64>(qkv, out, lse, B, T, H, st);
     if (hd == 72) return launch_attn_bf16<72>(qkv, out, lse, B, T, H, st);
     set_error("attention_fwd(bf16): head dim %d not supported (64, 72)", hd);

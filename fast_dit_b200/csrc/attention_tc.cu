@@ -1,0 +1,332 @@
+// attention_tc.cu — fused multi-head attention forward on the 5th-generation tensor cores, for the DiT
+// sequence lengths that fit one score tile: T = 128 or 256 tokens (256 px / patch 2), head dim 64..80.
+//
+//   out = softmax(q kᵀ / sqrt(hd)) v     per (image b, head h), non-causal, read straight from the token-major
+//   qkv matrix of the QKV GEMM and written into the token-major matrix the out-projection reads.
+//
+// With T <= 256 the whole score row of a query fits tensor memory (128 lanes x 256 f32 columns), so there is
+// no online-softmax rescaling: S = Q Kᵀ is produced by tcgen05.mma into TMEM, each softmax thread owns one
+// query row (two passes over its TMEM row: max, then exp/sum), P is written back to TMEM as packed bf16 over the
+// columns S occupied, and O = P V is a second tcgen05.mma whose A operand is read from TMEM.
+//
+// One persistent CTA per SM loops over (b, h) work items:
+//   warps 0-3  softmax + output of query tile 0 (rows 0..127 of the head)     } ping-pong: while one group
+//   warps 4-7  softmax + output of query tile 1 (rows 128..255, if T = 256)   } exponentiates, the other's MMAs run
+//   warp 8     TMA producer: Q tiles, K and V of the NEXT item into a 2-stage ring while this one computes
+//   warp 9     MMA issuer (one elected lane) + TMEM allocation
+// hd = 72 (DiT-XL) is handled without padding copies: the TMA tensor map is 3-D {hd, 3H heads, tokens}, the first
+// 64 channels land as a 128-byte-swizzled tile and channels 64..79 as a second, 32-byte-swizzled tile whose
+// columns >= hd are zero-filled by TMA (out of bounds in dimension 0); each gets its own tcgen05.mma.
+#include "common.cuh"
+
+namespace ditb200 {
+
+constexpr int kAtQ = 128;               // queries per tile = TMEM lanes
+constexpr int kAtThreads = 320;         // 8 softmax warps + producer + MMA
+constexpr int kAtRegion = 256;          // TMEM columns per query tile: S (<=256 f32) / P (<=128) + O (80)
+constexpr int kAtOCol = 128;            // O accumulator offset inside the region (P occupies [0,128))
+
+struct AttnSmem {
+  static constexpr int kQ0 = kAtQ * 128;        // Q channels 0..63, 128-byte rows
+  static constexpr int kQ1 = kAtQ * 32;         // Q channels 64..79, 32-byte rows
+  static constexpr int kK0 = 256 * 128, kK1 = 256 * 32, kV0 = 256 * 128, kV1 = 256 * 32;
+  static constexpr int kKV = kK0 + kK1 + kV0 + kV1;  // one ring stage (sized for T = 256)
+  static constexpr int oQ0 = 0, oQ1 = oQ0 + 2 * kQ0, oKV = oQ1 + 2 * kQ1;
+  static constexpr int oBars = oKV + 2 * kKV;
+  static constexpr int kBytes = oBars + 256 + 1024;
+};
+
+// 3-D tile load {c0 = channel, c1 = head slot, c2 = token}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// shared-memory matrix descriptors (hi word: SBO | version 1 | layout type; lo word: address >> 4 | LBO << 16)
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // 8-row groups every 1024 B
+constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);    // 8-row groups every 256 B
+__device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t smem_addr, uint32_t lbo_units) {
+  return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr & 0x3FFFFu) >> 4) | (lbo_units << 16));
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_k0,
+                   const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_q1,
+                   const __grid_constant__ CUtensorMap map_kv1, __nv_bfloat16* __restrict__ out,
+                   float* __restrict__ lse, const int B, const int T, const int H, const int hd,
+                   const float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::oBars);
+  uint64_t* q_full = bars;          // [2]  TMA -> MMA      (per query tile)
+  uint64_t* q_empty = bars + 2;     // [2]  MMA -> TMA
+  uint64_t* kv_full = bars + 4;     // [2]  TMA -> MMA      (ring stage)
+  uint64_t* kv_empty = bars + 6;    // [2]  MMA -> TMA
+  uint64_t* s_full = bars + 8;      // [2]  MMA -> softmax  (S tile in TMEM)
+  uint64_t* p_full = bars + 10;     // [2]  softmax -> MMA  (P written, 128 arrivals)
+  uint64_t* o_full = bars + 12;     // [2]  MMA -> softmax  (O tile in TMEM)
+  uint64_t* s_free = bars + 14;     // [2]  softmax -> MMA  (region drained, 128 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqt = T / kAtQ;          // query tiles per head: 1 or 2
+  const bool has_c1 = hd > 64;       // second channel chunk (64..79)
+  const int D = H * hd;
+  const int n_items = B * H;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q0), tma_prefetch_desc(&map_k0), tma_prefetch_desc(&map_v0);
+    tma_prefetch_desc(&map_q1), tma_prefetch_desc(&map_kv1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1), mbar_init(&q_empty[i], 1), mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1), mbar_init(&p_full[i], 128), mbar_init(&o_full[i], 1), mbar_init(&s_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ================================================================== TMA producer
+    const uint32_t q_bytes = (uint32_t)(AttnSmem::kQ0 + (has_c1 ? AttnSmem::kQ1 : 0));
+    const uint32_t kv_bytes = (uint32_t)(2 * T * 128 + (has_c1 ? 2 * T * 32 : 0));
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int b = w / H, h = w - b * H;
+      const int stage = it & 1;
+      const uint32_t kvpar = (it >> 1) & 1, par = it & 1;
+      const int tok0 = b * T;
+      uint8_t* kv = smem + AttnSmem::oKV + stage * AttnSmem::kKV;
+      mbar_wait(&kv_empty[stage], kvpar ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[stage], kv_bytes);
+        tma_load_3d(&map_k0, &kv_full[stage], kv, 0, H + h, tok0);
+        if (has_c1) tma_load_3d(&map_kv1, &kv_full[stage], kv + AttnSmem::kK0, 64, H + h, tok0);
+      }
+      __syncwarp();
+      for (int t = 0; t < nqt; ++t) {
+        mbar_wait(&q_empty[t], par ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&q_full[t], q_bytes);
+          tma_load_3d(&map_q0, &q_full[t], smem + AttnSmem::oQ0 + t * AttnSmem::kQ0, 0, h, tok0 + t * kAtQ);
+          if (has_c1) tma_load_3d(&map_q1, &q_full[t], smem + AttnSmem::oQ1 + t * AttnSmem::kQ1, 64, h, tok0 + t * kAtQ);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        uint8_t* v0 = kv + AttnSmem::kK0 + AttnSmem::kK1;
+        for (int kb = 0; kb < T / 64; ++kb)  // V channels 0..63: {64 channels x 64 keys} boxes, 8 KB each
+          tma_load_3d(&map_v0, &kv_full[stage], v0 + kb * 8192, 0, 2 * H + h, tok0 + kb * 64);
+        if (has_c1) tma_load_3d(&map_kv1, &kv_full[stage], v0 + AttnSmem::kV0, 64, 2 * H + h, tok0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ==================================================================== MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(kAtQ, (uint32_t)T);                 // S: 128 x T, both K-major
+    const uint32_t idesc_o64 = umma_idesc_bf16(kAtQ, 64) | (1u << 16);           // O[:, 0:64]: B = V, MN-major
+    const uint32_t idesc_o16 = umma_idesc_bf16(kAtQ, 16) | (1u << 16);           // O[:, 64:80]
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int stage = it & 1;
+      const uint32_t kvpar = (it >> 1) & 1, par = it & 1;
+      const uint32_t kv = smem_u32(smem + AttnSmem::oKV + stage * AttnSmem::kKV);
+      const uint32_t k0 = kv, k1 = kv + AttnSmem::kK0, v0 = k1 + AttnSmem::kK1, v1 = v0 + AttnSmem::kV0;
+      mbar_wait(&kv_full[stage], kvpar);
+      for (int t = 0; t < nqt; ++t) {
+        mbar_wait(&q_full[t], par);
+        mbar_wait(&s_free[t], par ^ 1u);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t d = tmem_base + (uint32_t)(t * kAtRegion);
+          const uint32_t q0 = smem_u32(smem + AttnSmem::oQ0 + t * AttnSmem::kQ0);
+          const uint32_t q1 = smem_u32(smem + AttnSmem::oQ1 + t * AttnSmem::kQ1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)  // 16 channels per step = 32 bytes inside the 128-byte swizzled row
+            umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
+          if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
+          umma_commit<1>(&s_full[t]);
+          umma_commit<1>(&q_empty[t]);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < nqt; ++t) {
+        mbar_wait(&p_full[t], par);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t p = tmem_base + (uint32_t)(t * kAtRegion);
+          const uint32_t d = p + kAtOCol;
+          for (int ks = 0; ks < T / 16; ++ks) {  // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V
+            umma_bf16_ts(d, p + 8 * ks, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, ks > 0);
+            if (has_c1) umma_bf16_ts(d + 64, p + 8 * ks, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, ks > 0);
+          }
+          umma_commit<1>(&o_full[t]);
+          if (t == nqt - 1) umma_commit<1>(&kv_empty[stage]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =================================================== softmax + output, one thread per query row
+    const int t = warp >> 2, quarter = warp & 3;
+    if (t < nqt) {
+      const int row = quarter * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kAtRegion);
+      const int nch = T / 32;  // 32-key chunks of the score row
+      const int hd8 = hd / 8;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        const int b = w / H, h = w - b * H;
+        const uint32_t par = it & 1;
+        mbar_wait(&s_full[t], par);
+        tcgen05_fence_after();
+        // ---- pass 1: row maximum of the raw scores
+        float mx = -INFINITY;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + 32 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+        }
+        // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as packed bf16 (in place)
+        const float msc = mx * scale_log2e;
+        float sum = 0.f;
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + 32 * c, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -msc));
+            sum += p0 + p1;
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(trow + 16 * c, pk);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&p_full[t]);
+        // ---- output: O / sum -> bf16 -> out[b*T + q, h*hd ...]
+        mbar_wait(&o_full[t], par);
+        tcgen05_fence_after();
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* orow = out + ((size_t)b * T + t * kAtQ + row) * D + h * hd;
+        for (int c = 0; c < 3; ++c) {  // 80 accumulator columns as 32 + 32 + 16
+          if (c * 32 >= hd) break;
+          uint32_t v[32];
+          if (c < 2) tmem_ld_32x32(trow + kAtOCol + 32 * c, v);
+          else {
+            uint32_t v16[16];
+            tmem_ld_32x16(trow + kAtOCol + 64, v16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v16[j];
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c * 4 + g < hd8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+              pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+              pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+              pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+              *reinterpret_cast<uint4*>(orow + (c * 4 + g) * 8) = pk;
+            }
+          }
+        }
+        tcgen05_fence_before();
+        mbar_arrive(&s_free[t]);
+        if (lse != nullptr)
+          lse[((size_t)b * H + h) * T + t * kAtQ + row] = (msc + log2f(sum)) * 0.6931471805599453f;
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// 3-D bf16 tensor map over qkv viewed as {hd channels, 3H head slots, B*T tokens}
+static int make_tmap_qkv(CUtensorMap* map, const void* base, int hd, int H, uint64_t tokens, uint32_t box_ch,
+                         uint32_t box_tok, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("attention: ditb200_init() has not been called");
+    return DITB200_ENOINIT;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)hd, (cuuint64_t)(3 * H), tokens};
+  cuuint64_t strides[2] = {(cuuint64_t)hd * 2, (cuuint64_t)3 * H * hd * 2};
+  cuuint32_t box[3] = {box_ch, 1, box_tok};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention: cuTensorMapEncodeTiled failed with CUresult %d (hd=%d H=%d box=%ux%u)", (int)r, hd, H,
+              box_ch, box_tok);
+    return DITB200_EINVAL;
+  }
+  return 0;
+}
+
+bool attn_fwd_tc_supported(int T, int hd) { return (T == 128 || T == 256) && hd % 8 == 0 && hd >= 64 && hd <= 80; }
+
+int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st) {
+  DITB_REQUIRE(is_initialised(), DITB200_ENOINIT, "attention: ditb200_init() has not been called");
+  CUtensorMap mq0, mk0, mv0, mq1, mkv1;
+  const uint64_t tokens = (uint64_t)B * T;
+  int rc;
+  if ((rc = make_tmap_qkv(&mq0, qkv, hd, H, tokens, 64, kAtQ, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_qkv(&mk0, qkv, hd, H, tokens, 64, (uint32_t)T, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_qkv(&mv0, qkv, hd, H, tokens, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_qkv(&mq1, qkv, hd, H, tokens, 16, kAtQ, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_tmap_qkv(&mkv1, qkv, hd, H, tokens, 16, (uint32_t)T, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kBytes);
+    if (e != cudaSuccess) return check_cuda(e, "attention_fwd(tcgen05) smem attribute");
+    attr_set = true;
+  }
+  int grid = num_sms();
+  if (grid > B * H) grid = B * H;
+  const float scale_log2e = (float)(1.4426950408889634 / sqrt((double)hd));
+  attn_fwd_tc_kernel<<<grid, kAtThreads, AttnSmem::kBytes, st>>>(mq0, mk0, mv0, mq1, mkv1,
+                                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd,
+                                                                 scale_log2e);
+  DITB_LAUNCH_CHECK("attention_fwd(tcgen05)");
+  return 0;
+}
+
+}  // namespace ditb200
