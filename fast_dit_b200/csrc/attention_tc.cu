@@ -32,7 +32,9 @@ struct AttnSmem {
   static constexpr int kK0 = 256 * 128, kK1 = 256 * 32, kV0 = 256 * 128, kV1 = 256 * 32;
   static constexpr int kKV = kK0 + kK1 + kV0 + kV1;  // one ring stage (sized for T = 256)
   static constexpr int oQ0 = 0, oQ1 = oQ0 + 2 * kQ0, oKV = oQ1 + 2 * kQ1;
-  static constexpr int oBars = oKV + 2 * kKV;
+  static constexpr int kStg = 32 * 64;           // per softmax warp: 32 rows x 32 bf16 output staging
+  static constexpr int oStg = oKV + 2 * kKV;
+  static constexpr int oBars = oStg + 8 * kStg;
   static constexpr int kBytes = oBars + 256 + 1024;
 };
 
@@ -154,44 +156,63 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
     const uint32_t idesc_s = umma_idesc_bf16(kAtQ, (uint32_t)T);                 // S: 128 x T, both K-major
     const uint32_t idesc_o64 = umma_idesc_bf16(kAtQ, 64) | (1u << 16);           // O[:, 0:64]: B = V, MN-major
     const uint32_t idesc_o16 = umma_idesc_bf16(kAtQ, 16) | (1u << 16);           // O[:, 64:80]
+    // Issue order (per query tile t, items i = 0, 1, ...):  S_t(0) ... then  O_t(i), S_t(i+1)  alternating over t.
+    // Putting S_t(i+1) directly behind O_t(i) lets softmax group t start on its next tile while the other group
+    // is still exponentiating: the MUFU pipe, which bounds this kernel, never waits for the tensor pipe.
+    auto issue_s = [&](int t, int stage) {
+      const uint32_t kv = smem_u32(smem + AttnSmem::oKV + stage * AttnSmem::kKV);
+      const uint32_t k0 = kv, k1 = kv + AttnSmem::kK0;
+      const uint32_t d = tmem_base + (uint32_t)(t * kAtRegion);
+      const uint32_t q0 = smem_u32(smem + AttnSmem::oQ0 + t * AttnSmem::kQ0);
+      const uint32_t q1 = smem_u32(smem + AttnSmem::oQ1 + t * AttnSmem::kQ1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)  // 16 channels per step = 32 bytes inside the 128-byte swizzled row
+        umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
+      if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
+      umma_commit<1>(&s_full[t]);
+      umma_commit<1>(&q_empty[t]);
+    };
+    auto issue_o = [&](int t, int stage, bool last) {
+      const uint32_t kv = smem_u32(smem + AttnSmem::oKV + stage * AttnSmem::kKV);
+      const uint32_t v0 = kv + AttnSmem::kK0 + AttnSmem::kK1, v1 = v0 + AttnSmem::kV0;
+      const uint32_t p = tmem_base + (uint32_t)(t * kAtRegion);
+      const uint32_t d = p + kAtOCol;
+      for (int ks = 0; ks < T / 16; ++ks) {  // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V
+        umma_bf16_ts(d, p + 8 * ks, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, ks > 0);
+        if (has_c1) umma_bf16_ts(d + 64, p + 8 * ks, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, ks > 0);
+      }
+      umma_commit<1>(&o_full[t]);
+      if (last) umma_commit<1>(&kv_empty[stage]);
+    };
+    if ((int)blockIdx.x < n_items) {  // prologue: the score tiles of this CTA's first item
+      mbar_wait(&kv_full[0], 0u);
+      for (int t = 0; t < nqt; ++t) {
+        mbar_wait(&q_full[t], 0u);
+        tcgen05_fence_after();
+        if (elect_one()) issue_s(t, 0);
+        __syncwarp();
+      }
+    }
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       const int stage = it & 1;
-      const uint32_t kvpar = (it >> 1) & 1, par = it & 1;
-      const uint32_t kv = smem_u32(smem + AttnSmem::oKV + stage * AttnSmem::kKV);
-      const uint32_t k0 = kv, k1 = kv + AttnSmem::kK0, v0 = k1 + AttnSmem::kK1, v1 = v0 + AttnSmem::kV0;
-      mbar_wait(&kv_full[stage], kvpar);
-      for (int t = 0; t < nqt; ++t) {
-        mbar_wait(&q_full[t], par);
-        mbar_wait(&s_free[t], par ^ 1u);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t d = tmem_base + (uint32_t)(t * kAtRegion);
-          const uint32_t q0 = smem_u32(smem + AttnSmem::oQ0 + t * AttnSmem::kQ0);
-          const uint32_t q1 = smem_u32(smem + AttnSmem::oQ1 + t * AttnSmem::kQ1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)  // 16 channels per step = 32 bytes inside the 128-byte swizzled row
-            umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
-          if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
-          umma_commit<1>(&s_full[t]);
-          umma_commit<1>(&q_empty[t]);
-        }
-        __syncwarp();
-      }
+      const uint32_t par = it & 1;
+      const bool has_next = w + (int)gridDim.x < n_items;
+      const int nstage = (it + 1) & 1;
+      const uint32_t nkvpar = ((it + 1) >> 1) & 1, npar = (it + 1) & 1;
       for (int t = 0; t < nqt; ++t) {
         mbar_wait(&p_full[t], par);
         tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t p = tmem_base + (uint32_t)(t * kAtRegion);
-          const uint32_t d = p + kAtOCol;
-          for (int ks = 0; ks < T / 16; ++ks) {  // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V
-            umma_bf16_ts(d, p + 8 * ks, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, ks > 0);
-            if (has_c1) umma_bf16_ts(d + 64, p + 8 * ks, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, ks > 0);
-          }
-          umma_commit<1>(&o_full[t]);
-          if (t == nqt - 1) umma_commit<1>(&kv_empty[stage]);
-        }
+        if (elect_one()) issue_o(t, stage, t == nqt - 1);
         __syncwarp();
+        if (has_next) {
+          if (t == 0) mbar_wait(&kv_full[nstage], nkvpar);
+          mbar_wait(&q_full[t], npar);
+          mbar_wait(&s_free[t], par);  // group t has pulled O_t(i) out of the region
+          tcgen05_fence_after();
+          if (elect_one()) issue_s(t, nstage);
+          __syncwarp();
+        }
       }
     }
   } else {
@@ -201,72 +222,101 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const int row = quarter * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kAtRegion);
       const int nch = T / 32;  // 32-key chunks of the score row
-      const int hd8 = hd / 8;
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
         const uint32_t par = it & 1;
         mbar_wait(&s_full[t], par);
         tcgen05_fence_after();
-        // ---- pass 1: row maximum of the raw scores
+        // ---- pass 1: row maximum of the raw scores (TMEM loads one chunk ahead of the compare chain)
+        uint32_t va[32], vb[32];
         float mx = -INFINITY;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(trow + 32 * c, v);
+        tmem_ld_32x32(trow, va);
+        for (int c = 0; c < nch; c += 2) {
           tmem_ld_wait();
+          tmem_ld_32x32(trow + 32 * (c + 1), vb);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-        }
-        // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as packed bf16 (in place)
-        const float msc = mx * scale_log2e;
-        float sum = 0.f;
-        for (int c = 0; c < nch; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(trow + 32 * c, v);
+          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[j]), __uint_as_float(va[j + 1])));
           tmem_ld_wait();
-          uint32_t pk[16];
+          tmem_ld_32x32(trow + (c + 2 < nch ? 32 * (c + 2) : 0), va);  // last round: chunk 0 again, for pass 2
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[j]), __uint_as_float(vb[j + 1])));
+        }
+        // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as packed bf16 (in place: the
+        //      16 columns chunk c of P lands on were read as part of S chunk c/2 <= c)
+        const float msc = mx * scale_log2e;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[16];
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(trow + 32 * (c + 1), vb);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -msc));
-            sum += p0 + p1;
+            const float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * j]), scale_log2e, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * j + 1]), scale_log2e, -msc));
+            sum0 += p0, sum1 += p1;
             pk[j] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x16(trow + 16 * c, pk);
+          tmem_ld_wait();
+          if (c + 2 < nch) tmem_ld_32x32(trow + 32 * (c + 2), va);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[2 * j]), scale_log2e, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[2 * j + 1]), scale_log2e, -msc));
+            sum0 += p0, sum1 += p1;
+            pk[j] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(trow + 16 * (c + 1), pk);
         }
+        const float sum = sum0 + sum1;
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&p_full[t]);
-        // ---- output: O / sum -> bf16 -> out[b*T + q, h*hd ...]
+        // ---- output: O / sum -> bf16, transposed through this warp's staging buffer so that the global stores
+        //      cover whole 64-byte row segments (8 rows per instruction) instead of 32 scattered 16-byte pieces
         mbar_wait(&o_full[t], par);
         tcgen05_fence_after();
+        uint32_t o2[16];
+        tmem_ld_32x32(trow + kAtOCol, va);
+        tmem_ld_32x32(trow + kAtOCol + 32, vb);
+        if (has_c1) tmem_ld_32x16(trow + kAtOCol + 64, o2);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&s_free[t]);  // the accumulators are in registers: the region may take the next score tile
         const float inv = 1.0f / sum;
-        __nv_bfloat16* orow = out + ((size_t)b * T + t * kAtQ + row) * D + h * hd;
-        for (int c = 0; c < 3; ++c) {  // 80 accumulator columns as 32 + 32 + 16
-          if (c * 32 >= hd) break;
-          uint32_t v[32];
-          if (c < 2) tmem_ld_32x32(trow + kAtOCol + 32 * c, v);
-          else {
-            uint32_t v16[16];
-            tmem_ld_32x16(trow + kAtOCol + 64, v16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v16[j];
-          }
-          tmem_ld_wait();
+        uint8_t* stg = smem + AttnSmem::oStg + warp * AttnSmem::kStg;
+        __nv_bfloat16* obase = out + ((size_t)b * T + t * kAtQ + quarter * 32) * D + h * hd;
+        auto flush = [&](const uint32_t* v, int ncol, int col0) {  // ncol in {32, 16} accumulator columns
+          uint8_t* my = stg + lane * 64;
+          const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (c * 4 + g < hd8) {
-              uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
-              pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
-              pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
-              pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-              *reinterpret_cast<uint4*>(orow + (c * 4 + g) * 8) = pk;
+            if (g * 8 < ncol) {
+              uint4 q4;
+              q4.x = pack_bf16x2(__uint_as_float(v[8 * g]) * inv, __uint_as_float(v[8 * g + 1]) * inv);
+              q4.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
+              q4.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
+              q4.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
+              *reinterpret_cast<uint4*>(my + ((g ^ sw) << 4)) = q4;
             }
           }
-        }
-        tcgen05_fence_before();
-        mbar_arrive(&s_free[t]);
+          __syncwarp();
+          const int g = lane & 3;
+          const int col = col0 + g * 8;
+          if (g * 8 < ncol && col < hd) {
+#pragma unroll
+            for (int pss = 0; pss < 4; ++pss) {
+              const int r = pss * 8 + (lane >> 2);
+              const uint4 q4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((g ^ ((r >> 1) & 3)) << 4));
+              *reinterpret_cast<uint4*>(obase + (size_t)r * D + col) = q4;
+            }
+          }
+          __syncwarp();
+        };
+        flush(va, 32, 0);
+        flush(vb, 32, 32);
+        if (has_c1) flush(o2, 16, 64);
         if (lse != nullptr)
           lse[((size_t)b * H + h) * T + t * kAtQ + row] = (msc + log2f(sum)) * 0.6931471805599453f;
       }
