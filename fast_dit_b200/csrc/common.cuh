@@ -121,11 +121,11 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
-// arrive on the barrier at the same smem offset in CTA 0 (the leader) of the cluster
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+// arrive on the barrier at the same smem offset in CTA `leader_rank` (the pair's leader) of the cluster
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar, uint32_t leader_rank = 0) {
   // default semantics on purpose: an explicit .release.cluster costs a MEMBAR.ALL.CTA + ERRBAR
   // (waits for every outstanding global store of the thread) in front of each arrive
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, 0)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(bar, leader_rank)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -179,12 +179,25 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
 }
 // 2-D tile load issued by either CTA of a pair; completion bytes go to the LEADER CTA's barrier
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst,
-                                                 int c0, int c1) {
-  const uint32_t bar_addr = mapa_u32(bar, 0);
+                                                 int c0, int c1, uint32_t leader_rank = 0) {
+  const uint32_t bar_addr = mapa_u32(bar, leader_rank);
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 2-D tile load multicast to the CTAs in `mask` (same smem offset in each); in every destination CTA the
+// completion bytes go to the barrier at `bar`'s offset in that CTA's PAIR LEADER (peer bit of the shared-window
+// address cleared, as the cta_group::2 form defines it)
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                    uint16_t mask) {
+  const uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
 
@@ -240,7 +253,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
 }
 // all previously issued MMAs of this thread arrive on `bar` when done (implies fence::before_thread_sync)
 template <int kCtaGroup>
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint16_t mask = 3) {
   if constexpr (kCtaGroup == 1)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
@@ -249,7 +262,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
         "[%0], %1;" ::"r"(smem_u32(bar)),
-        "h"((uint16_t)3)
+        "h"(mask)
         : "memory");
 }
 

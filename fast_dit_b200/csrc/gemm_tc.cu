@@ -245,7 +245,11 @@ struct TileSched {
   }
 };
 
-template <int kCG, int BN>
+// kMC = CTA pairs per cluster.  With kMC == 2 (cluster of 4 CTAs) the two pairs work on vertically adjacent
+// 256-row tiles of the same tile column and SHARE the B tile: every CTA fetches one quarter of it and TMA
+// multicasts that quarter to the CTA holding the same B half in the other pair, so a 512 x 256 super-tile moves
+// 96 KB per k-block out of L2 instead of 128 KB.  The L2 -> SM fabric, not the tensor pipe, bounds these GEMMs.
+template <int kCG, int BN, int kMC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
@@ -266,15 +270,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
+  const uint32_t cl_rank = (kCG == 2) ? cluster_ctarank() : 0u;  // rank in the cluster: pair = rank / 2
+  const uint32_t cta_rank = cl_rank & 1u;                        // rank inside the CTA pair
+  const uint32_t pair = cl_rank >> 1, lead_rank = cl_rank & ~1u;
   const bool leader = cta_rank == 0;
+  static_assert(kMC == 1 || kCG == 2, "multicast clusters are built from CTA pairs");
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);    // one arrive.expect_tx (leader CTA) covering every CTA's bytes
-      mbar_init(&empty[s], 1);   // one tcgen05.commit per phase
+      mbar_init(&empty[s], kMC);  // one tcgen05.commit per phase from every pair that reads (a copy of) the slot
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -292,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int k_blocks = (K + kBK - 1) / kBK;
   const int kb_per = (k_blocks + split_k - 1) / split_k;
   TileSched sched;
-  sched.init(M, N, tile_m, BN, part_cols, split_k, (int)gridDim.x / kCG, (int)blockIdx.x / kCG);
+  sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC));
   int m_blk, n_blk, ncols, split;
 
   // Producer and MMA roles run warp-uniform loops (every lane waits on the barriers) and elect one
@@ -305,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     while (sched.next(BN, m_blk, n_blk, ncols, split)) {
-      const int row_a = m_blk * tile_m + (int)cta_rank * kBM;
+      const int row_a = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM;
       const int row_b = n_blk * BN + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -320,22 +327,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (leader) mbar_arrive_expect_tx(&full[stage], kCG * Cfg::kStageBytes);
           if (!a_mn) {
             if constexpr (kCG == 1) tma_load_2d(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
-            else tma_load_2d_pair(&tma_a, &full[stage], dst_a, kb * kBK, row_a);
+            else tma_load_2d_pair(&tma_a, &full[stage], dst_a, kb * kBK, row_a, lead_rank);
           } else {
 #pragma unroll
             for (int c = 0; c < kBM / 64; ++c) {
               if constexpr (kCG == 1) tma_load_2d(&tma_a, &full[stage], dst_a + c * kMnChunkBytes, row_a + 64 * c, kb * kBK);
-              else tma_load_2d_pair(&tma_a, &full[stage], dst_a + c * kMnChunkBytes, row_a + 64 * c, kb * kBK);
+              else tma_load_2d_pair(&tma_a, &full[stage], dst_a + c * kMnChunkBytes, row_a + 64 * c, kb * kBK, lead_rank);
             }
           }
-          if (!b_mn) {
+          if constexpr (kMC == 2) {
+            // this CTA's quarter of the B tile (box = kBRows / 2 rows), delivered to both CTAs holding this half
+            constexpr int kQRows = Cfg::kBRows / 2;
+            tma_load_2d_pair_mc(&tma_b, &full[stage], dst_b + (int)pair * (Cfg::kBBytes / 2), kb * kBK,
+                                row_b + (int)pair * kQRows, (uint16_t)(0x5u << cta_rank));
+          } else if (!b_mn) {
             if constexpr (kCG == 1) tma_load_2d(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
-            else tma_load_2d_pair(&tma_b, &full[stage], dst_b, kb * kBK, row_b);
+            else tma_load_2d_pair(&tma_b, &full[stage], dst_b, kb * kBK, row_b, lead_rank);
           } else {
 #pragma unroll
             for (int c = 0; c < Cfg::kBRows / 64; ++c) {
               if constexpr (kCG == 1) tma_load_2d(&tma_b, &full[stage], dst_b + c * kMnChunkBytes, row_b + 64 * c, kb * kBK);
-              else tma_load_2d_pair(&tma_b, &full[stage], dst_b + c * kMnChunkBytes, row_b + 64 * c, kb * kBK);
+              else tma_load_2d_pair(&tma_b, &full[stage], dst_b + c * kMnChunkBytes, row_b + 64 * c, kb * kBK, lead_rank);
             }
           }
         }
@@ -378,8 +390,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_kstep * k);
               umma_bf16<kCG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
-            umma_commit<kCG>(&empty[stage]);  // frees this smem slot (in both CTAs) when the MMAs retire
-            if (kb == kb1 - 1) umma_commit<kCG>(&tmem_full[acc]);
+            // frees this smem slot when the MMAs retire: in both CTAs of the pair, and (kMC == 2) in the other
+            // pair too, whose multicast loads write into this pair's copy of the B tile
+            umma_commit<kCG>(&empty[stage], (uint16_t)(kMC == 2 ? 0xFu : 0x3u));
+            if (kb == kb1 - 1) umma_commit<kCG>(&tmem_full[acc], (uint16_t)(0x3u << (2 * pair)));
           }
           __syncwarp();
           if (++stage == kStages) stage = 0, phase ^= 1u;
@@ -395,7 +409,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int row0 = m_blk * tile_m + (int)cta_rank * kBM + quarter * 32;  // first row of this warp's lane quarter
+      const int row0 = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM + quarter * 32;  // first row of this warp's lane quarter
       if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID) {
         // The residual tile does not depend on the MMAs: pull this warp's 32 x (ncols/2) block towards L2
         // while the accumulators are still being produced, so the epilogue loads below do not pay HBM latency.
@@ -438,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc]);
+        if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc], lead_rank);
       }
     }
   }
@@ -485,7 +499,7 @@ static int narrow_cols(int N, int bn, int cg, int trans_w) {
   return np;
 }
 
-template <int kCG, int BN>
+template <int kCG, int BN, int kMC = 1>
 static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) {
   using Cfg = TcCfg<kCG, BN>;
   CUtensorMap ta, tb;
@@ -494,7 +508,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   if (!a->trans_a) rc = make_tmap_2d(&ta, a->a, (uint64_t)a->M, (uint64_t)a->K, kBM, kBK);
   else rc = make_tmap_2d(&ta, a->a, (uint64_t)a->K, (uint64_t)a->M, kBK, 64);
   if (rc) return rc;
-  if (!a->trans_w) rc = make_tmap_2d(&tb, a->w, (uint64_t)a->N, (uint64_t)a->K, Cfg::kBRows, kBK);
+  if (!a->trans_w) rc = make_tmap_2d(&tb, a->w, (uint64_t)a->N, (uint64_t)a->K, Cfg::kBRows / kMC, kBK);
   else rc = make_tmap_2d(&tb, a->w, (uint64_t)a->K, (uint64_t)a->N, kBK, 64);
   if (rc) return rc;
   EpiParams ep;
@@ -506,7 +520,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   ep.atomic = (split_k > 1 || a->accumulate) ? 1 : 0;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kCG, BN>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kCG, BN, kMC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return check_cuda(e, "gemm_tc smem attribute");
     attr_set = true;
@@ -515,25 +529,37 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
     cudaError_t e = cudaMemsetAsync(a->out, 0, (size_t)a->M * a->N * sizeof(float), st);
     if (e != cudaSuccess) return check_cuda(e, "gemm_tc split-K memset");
   }
-  const int tile_m = kBM * kCG;
+  const int tile_m = kBM * kCG * kMC;  // rows per cluster work unit
   const int units = ((a->M + tile_m - 1) / tile_m) * ((a->N + BN - 1) / BN) * split_k;
-  int ctas = num_sms() / kCG;
-  if (ctas > units) ctas = units;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(ctas * kCG));
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.x = kCG * kMC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN>, ta, tb, ep, a->M, a->N, a->K,
-                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k,
-                                     narrow_cols(a->N, BN, kCG, a->trans_w));
+  int clusters = num_sms() / (kCG * kMC);
+  if constexpr (kMC > 1) {
+    // clusters of 4 cannot tile every GPC: ask how many are co-resident (a persistent kernel must not queue any)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<kCG, BN, kMC>, &cfg);
+      if (e != cudaSuccess) return check_cuda(e, "gemm_tc cluster occupancy");
+      max_clusters = n > 0 ? n : 1;
+    }
+    if (clusters > max_clusters) clusters = max_clusters;
+  }
+  if (clusters > units) clusters = units;
+  cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
+  const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, ep, a->M, a->N, a->K,
+                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
 }
@@ -627,6 +653,13 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   }
   DITB_REQUIRE(!a->trans_w || (bn / cg) % 64 == 0, DITB200_EINVAL,
                "gemm(tcgen05): trans_w needs tile_n / cta_group to be a multiple of 64 (got %d / %d)", bn, cg);
+  if (cg == 4) {  // two CTA pairs per cluster sharing the B tile by TMA multicast (K-major B only)
+    DITB_REQUIRE(!a->trans_w && a->M > kBM, DITB200_EINVAL, "gemm(tcgen05): cta_group 4 needs a K-major w and M > 128");
+    if (bn == 256) return launch_cfg<2, 256, 2>(a, split_k, st);
+    if (bn == 128) return launch_cfg<2, 128, 2>(a, split_k, st);
+    set_error("gemm(tcgen05): cta_group 4 supports tile_n 128 / 256 (got %d)", bn);
+    return DITB200_EINVAL;
+  }
 #define TC_CASE(CG, BN_)                   \
   if (cg == CG && bn == BN_) return launch_cfg<CG, BN_>(a, split_k, st);
   TC_CASE(1, 128)

@@ -167,6 +167,36 @@ def test_gemm_tcgen05_bias(ops, dev, M, N, K, cta_group, tile_n):
     assert rel_l2(y16.float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(1024, 1152, 1152), (1000, 3456, 1152), (2048, 512, 4608), (300, 200, 72)])
+def test_gemm_tcgen05_multicast_cluster(ops, dev, M, N, K, tile_n):
+    """cta_group=4: two CTA pairs per cluster share the B tile through TMA multicast (ragged M: the second
+    pair's rows may lie past the matrix)."""
+    g = torch.Generator(device=dev).manual_seed(15)
+    a = (torch.randn(M, K, device=dev, generator=g)).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    ref = _gemm_ref(a, w, bias, 0)
+    y32 = ops.gemm(a, w, bias, out_dtype=torch.float32, tile_n=tile_n, cta_group=4)
+    assert rel_l2(y32, ref) < 1e-5
+    same = ops.gemm(a, w, bias, out_dtype=torch.float32, tile_n=tile_n, cta_group=2)
+    assert torch.equal(y32, same), "same tile shape, same accumulation order: bit-identical to the pair kernel"
+
+
+def test_gemm_tcgen05_narrow_last_column_matches_full_tiles(ops, dev):
+    """N = 1152 with 256-wide tiles ends in a 128-wide column that runs as a narrow tcgen05.mma under the
+    LPT schedule; the result must be bit-identical to covering N with 128-wide tiles (same k order)."""
+    g = torch.Generator(device=dev).manual_seed(16)
+    M, N, K = 4096, 1152, 1152
+    a = (torch.randn(M, K, device=dev, generator=g)).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    y256 = ops.gemm(a, w, bias, out_dtype=torch.float32, tile_n=256, cta_group=2)
+    y128 = ops.gemm(a, w, bias, out_dtype=torch.float32, tile_n=128, cta_group=2)
+    assert torch.equal(y256, y128)
+    assert rel_l2(y256, _gemm_ref(a, w, bias, 0)) < 1e-5
+
+
 @pytest.mark.parametrize("epi", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K,T", [(1024, 1152, 1152, 256), (768, 1536, 384, 64), (200, 384, 1536, 16)])
 def test_gemm_tcgen05_epilogues(ops, dev, M, N, K, T, epi):
@@ -223,6 +253,26 @@ def test_attention_bf16(ops, dev, B, T, H, hd):
     q, k, _ = qkv.double().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
     ref_lse = torch.logsumexp(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
     assert rel_l2(lse, ref_lse) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(1, 128, 1, 64), (3, 128, 5, 72), (20, 256, 16, 72), (40, 128, 12, 64),
+                                      (11, 256, 16, 80)])
+def test_attention_tcgen05_persistent(ops, dev, B, T, H, hd):
+    """The tcgen05/TMEM forward (T in {128, 256}): more (image, head) items than SMs, so every CTA runs
+    several items through its K/V ring and both barrier phases; hd 72/80 exercise the zero-filled second
+    channel chunk; scores scaled up so the row maximum matters."""
+    g = torch.Generator(device=dev).manual_seed(18)
+    qkv = (torch.randn(B * T, 3 * H * hd, device=dev, generator=g) * 2.0).bfloat16()
+    lse = torch.empty(B, H, T, device=dev)
+    o = ops.attention(qkv, B, T, H, hd, lse=lse)
+    assert torch.isfinite(o.float()).all()
+    ref = _attn_ref(qkv.float(), B, T, H, hd)
+    assert rel_l2(o.float(), ref) < 6e-3
+    q, k, _ = qkv.double().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    ref_lse = torch.logsumexp(q @ k.transpose(-1, -2) / math.sqrt(hd), dim=-1)
+    assert rel_l2(lse, ref_lse) < 1e-4
+    again = ops.attention(qkv, B, T, H, hd)
+    assert torch.equal(o, again), "no atomics, fixed schedule: run-to-run identical"
 
 
 @pytest.mark.parametrize("p,Cout,T,D", [(2, 8, 256, 1152), (4, 8, 64, 768), (8, 8, 16, 384), (2, 4, 256, 384)])
