@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--trans-a", action="store_true")
     ap.add_argument("--split-k", type=int, default=0)
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--inplace", action="store_true", help="epi 2: update the residual stream in place (as the model does)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     M, N, K = a.m, a.n, a.k
@@ -40,9 +41,10 @@ def main():
         bias = torch.randn(N, device=dev, generator=g)
         kw = dict(bias=bias)
         if a.epi == 2:
-            kw.update(epilogue=L.EPI_BIAS_GATE_RESID, resid=torch.randn(M, N, device=dev, generator=g),
-                      gate=torch.randn(max(1, M // T), N, device=dev, generator=g), rows_per_gate=T,
-                      out=torch.empty(M, N, device=dev))
+            res = torch.randn(M, N, device=dev, generator=g)
+            kw.update(epilogue=L.EPI_BIAS_GATE_RESID, resid=res,
+                      gate=torch.randn(max(1, M // T), N, device=dev, generator=g) * 0.1, rows_per_gate=T,
+                      out=res if a.inplace else torch.empty(M, N, device=dev))
         elif a.epi == 1:
             kw.update(epilogue=L.EPI_BIAS_GELU, out=torch.empty(M, N, device=dev, dtype=torch.bfloat16))
         elif a.split_k > 1:
@@ -76,7 +78,8 @@ def main():
                 A, W, kw = sets[0]
                 kw2 = dict(kw)
                 if a.epi == 2:
-                    kw2["out"] = torch.empty(M, N, device=dev)
+                    res0 = kw["resid"].clone()
+                    kw2["out"] = kw["resid"] if a.inplace else torch.empty(M, N, device=dev)
                 got = ops.gemm(A, W, cta_group=cg, tile_n=bn, trans_a=a.trans_a, trans_w=a.trans_w, **kw2).float()
                 Af = A.float().t() if a.trans_a else A.float()
                 Wf = W.float() if a.trans_w else W.float().t()
@@ -84,7 +87,7 @@ def main():
                 if a.epi == 1:
                     ref = torch.nn.functional.gelu(ref, approximate="tanh")
                 if a.epi == 2:
-                    ref = kw["resid"] + kw["gate"].repeat_interleave(T, 0)[:M] * ref
+                    ref = res0 + kw["gate"].repeat_interleave(T, 0)[:M] * ref
                 err = float((got - ref).norm() / ref.norm())
                 print(f"  check cg={cg} bn={bn}: rel-L2 {err:.2e}")
             ms = time_it(lambda i: run(cg, bn, i))
