@@ -16,6 +16,7 @@ LIB_PATH = _PKG / "lib" / "libditb200.so"
 F32, BF16 = 0, 1
 ABI_VERSION = 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RESID, EPI_BIAS_SILU, EPI_MUL_DGELU = 0, 1, 2, 3, 4
+EPI_BIAS_GELU_DAUX, EPI_MUL_AUX = 5, 6
 GEMM_TCGEN05, GEMM_FP32 = 0, 1
 MEAN_EPSILON, MEAN_START_X = 0, 1
 VAR_LEARNED_RANGE, VAR_LEARNED, VAR_FIXED = 0, 1, 2

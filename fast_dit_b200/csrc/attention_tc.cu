@@ -285,10 +285,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         tcgen05_fence_before();
         mbar_arrive(&s_free[t]);  // the accumulators are in registers: the region may take the next score tile
         const float inv = 1.0f / sum;
-        uint8_t* stg = smem + AttnSmem::oStg + warp * AttnSmem::kStg;
+        const uint32_t stg = smem_u32(smem + AttnSmem::oStg) + (uint32_t)(warp * AttnSmem::kStg);
         __nv_bfloat16* obase = out + ((size_t)b * T + t * kAtQ + quarter * 32) * D + h * hd;
         auto flush = [&](const uint32_t* v, int ncol, int col0) {  // ncol in {32, 16} accumulator columns
-          uint8_t* my = stg + lane * 64;
+          const uint32_t my = stg + (uint32_t)lane * 64u;
           const int sw = (lane >> 1) & 3;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -298,7 +298,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
               q4.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]) * inv, __uint_as_float(v[8 * g + 3]) * inv);
               q4.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]) * inv, __uint_as_float(v[8 * g + 5]) * inv);
               q4.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]) * inv, __uint_as_float(v[8 * g + 7]) * inv);
-              *reinterpret_cast<uint4*>(my + ((g ^ sw) << 4)) = q4;
+              sts128(my + (uint32_t)((g ^ sw) << 4), q4.x, q4.y, q4.z, q4.w);
             }
           }
           __syncwarp();
@@ -308,7 +308,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
 #pragma unroll
             for (int pss = 0; pss < 4; ++pss) {
               const int r = pss * 8 + (lane >> 2);
-              const uint4 q4 = *reinterpret_cast<const uint4*>(stg + r * 64 + ((g ^ ((r >> 1) & 3)) << 4));
+              const uint4 q4 = lds128_u(stg + (uint32_t)(r * 64 + ((g ^ ((r >> 1) & 3)) << 4)));
               *reinterpret_cast<uint4*>(obase + (size_t)r * D + col) = q4;
             }
           }

@@ -85,11 +85,88 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(
   }
 }
 
+// Fixed-width variant (D = NV * 128): warp per row with the row of x and dh held in registers (each read from
+// HBM exactly once, like the forward kernel) and the per-column partial sums of dshift / dscale carried in
+// registers across the rows a warp owns; shared memory sees one reduction per CTA instead of eight atomics per
+// element.  CTA = 4 warps x kLnWarpRows consecutive tokens of ONE image.
+constexpr int kLnWarpRows = 4;
+template <int NV, typename TDh>
+__global__ void __launch_bounds__(128) ln_modulate_bwd_rows_kernel(
+    const TDh* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale, int mod_stride,
+    const float* __restrict__ stats, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
+    float* __restrict__ dscale, int dmod_stride, int T) {
+  constexpr int D = NV * 128;
+  __shared__ float red[2 * D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * (4 * kLnWarpRows) + warp * kLnWarpRows;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+  float4 a_sh[NV], a_sc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) a_sh[j] = a_sc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < kLnWarpRows; ++r) {
+    const int t = t0 + r;
+    if (t >= T) break;
+    const size_t row = (size_t)b * T + t;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    const float* xr = x + row * D;
+    const TDh* dr = dh + row * D;
+    float4 xv[NV], dv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      xv[j] = ldg_stream_f4(reinterpret_cast<const float4*>(xr) + lane + 32 * j);
+      dv[j] = load4(dr + 4 * (lane + 32 * j));
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 cv = __ldg(sc + lane + 32 * j);
+      // xv becomes xhat, the column sums take dh and dh * xhat, s1 / s2 the row means of g and g * xhat
+      xv[j].x = (xv[j].x - mean) * rstd, xv[j].y = (xv[j].y - mean) * rstd;
+      xv[j].z = (xv[j].z - mean) * rstd, xv[j].w = (xv[j].w - mean) * rstd;
+      a_sh[j].x += dv[j].x, a_sh[j].y += dv[j].y, a_sh[j].z += dv[j].z, a_sh[j].w += dv[j].w;
+      a_sc[j].x += dv[j].x * xv[j].x, a_sc[j].y += dv[j].y * xv[j].y;
+      a_sc[j].z += dv[j].z * xv[j].z, a_sc[j].w += dv[j].w * xv[j].w;
+      dv[j].x *= 1.f + cv.x, dv[j].y *= 1.f + cv.y, dv[j].z *= 1.f + cv.z, dv[j].w *= 1.f + cv.w;  // g
+      s1 += (dv[j].x + dv[j].y) + (dv[j].z + dv[j].w);
+      s2 += (dv[j].x * xv[j].x + dv[j].y * xv[j].y) + (dv[j].z * xv[j].z + dv[j].w * xv[j].w);
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+    float* dxr = dx + row * D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 o;
+      o.x = rstd * (dv[j].x - s1 - xv[j].x * s2), o.y = rstd * (dv[j].y - s1 - xv[j].y * s2);
+      o.z = rstd * (dv[j].z - s1 - xv[j].z * s2), o.w = rstd * (dv[j].w - s1 - xv[j].w * s2);
+      float4* dst = reinterpret_cast<float4*>(dxr) + lane + 32 * j;
+      if (accumulate) {
+        const float4 p = *dst;
+        o.x += p.x, o.y += p.y, o.z += p.z, o.w += p.w;
+      }
+      *dst = o;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    atomicAdd(&red[c], a_sh[j].x), atomicAdd(&red[c + 1], a_sh[j].y), atomicAdd(&red[c + 2], a_sh[j].z), atomicAdd(&red[c + 3], a_sh[j].w);
+    atomicAdd(&red[D + c], a_sc[j].x), atomicAdd(&red[D + c + 1], a_sc[j].y), atomicAdd(&red[D + c + 2], a_sc[j].z), atomicAdd(&red[D + c + 3], a_sc[j].w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dshift + (size_t)b * dmod_stride + i, red[i]);
+    atomicAdd(dscale + (size_t)b * dmod_stride + i, red[D + i]);
+  }
+}
+
 // ============================================================ gated residual, backward
 // x_out = x + gate[b] * y:  dy = dx_out * gate[b];  dgate[b] += sum_t dx_out * y;  dbias += sum_rows dy.
 // Thread = 4 columns, CTA = kGrRows tokens of one image: coalesced 128-bit row accesses, the
 // reductions over tokens stay in registers, one atomic per column per CTA.
-constexpr int kGrRows = 16;
+constexpr int kGrRows = 8;
 template <typename TY>
 __global__ void gate_resid_bwd_kernel(const float* __restrict__ dxo, const TY* __restrict__ y,
                                       const float* __restrict__ gate, int gate_stride, TY* __restrict__ dy,
@@ -101,18 +178,28 @@ __global__ void gate_resid_bwd_kernel(const float* __restrict__ dxo, const TY* _
   const int t0 = blockIdx.x * kGrRows, t1 = min(T, t0 + kGrRows);
   const float4 g = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_stride + c));
   float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
-  for (int t = t0; t < t1; ++t) {
-    const size_t off = ((size_t)b * T + t) * D + c;
-    const float4 d = load4(dxo + off), yy = load4(y + off);
-    const float4 o = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
-    store4(dy + off, o);
-    ag.x += d.x * yy.x, ag.y += d.y * yy.y, ag.z += d.z * yy.z, ag.w += d.w * yy.w;
-    ab.x += o.x, ab.y += o.y, ab.z += o.z, ab.w += o.w;
+  for (int tt = t0; tt < t1; tt += 8) {  // 8 rows of loads in flight per thread
+    float4 d[8], yy[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (tt + u < t1) {
+        const size_t off = ((size_t)b * T + tt + u) * D + c;
+        d[u] = load4(dxo + off), yy[u] = load4(y + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (tt + u < t1) {
+        const size_t off = ((size_t)b * T + tt + u) * D + c;
+        const float4 o = make_float4(d[u].x * g.x, d[u].y * g.y, d[u].z * g.z, d[u].w * g.w);
+        store4(dy + off, o);
+        ag.x += d[u].x * yy[u].x, ag.y += d[u].y * yy[u].y, ag.z += d[u].z * yy[u].z, ag.w += d[u].w * yy[u].w;
+        ab.x += o.x, ab.y += o.y, ab.z += o.z, ab.w += o.w;
+      }
+    }
   }
-  float* dg = dgate + (size_t)b * dgate_stride + c;
-  atomicAdd(dg, ag.x), atomicAdd(dg + 1, ag.y), atomicAdd(dg + 2, ag.z), atomicAdd(dg + 3, ag.w);
-  if (dbias != nullptr)
-    atomicAdd(dbias + c, ab.x), atomicAdd(dbias + c + 1, ab.y), atomicAdd(dbias + c + 2, ab.z), atomicAdd(dbias + c + 3, ab.w);
+  atomicAdd(reinterpret_cast<float4*>(dgate + (size_t)b * dgate_stride + c), ag);  // one 128-bit reduction
+  if (dbias != nullptr) atomicAdd(reinterpret_cast<float4*>(dbias + c), ab);
 }
 
 // ======================================================================== column sums
@@ -123,11 +210,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in,
   if (c >= C) return;
   const int r0 = blockIdx.y * kCsRows, r1 = min(R, r0 + kCsRows);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
-    const float4 v = load4(in + (size_t)r * C + c);
-    a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+  for (int rr = r0; rr < r1; rr += 8) {  // 8 rows of loads in flight per thread
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = (rr + u < r1) ? load4(in + (size_t)(rr + u) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a.x += v[u].x, a.y += v[u].y, a.z += v[u].z, a.w += v[u].w;
   }
-  atomicAdd(out + c, a.x), atomicAdd(out + c + 1, a.y), atomicAdd(out + c + 2, a.z), atomicAdd(out + c + 3, a.w);
+  atomicAdd(reinterpret_cast<float4*>(out + c), a);  // one 128-bit reduction
 }
 
 // ================================================================ label embed, backward
@@ -200,9 +291,32 @@ extern "C" int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float
   DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0 && B <= 65535, DITB200_EINVAL, "ln_modulate_bwd: bad shape");
   DITB_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(scale) && mod_stride % 4 == 0,
                DITB200_EALIGN, "ln_modulate_bwd: misaligned pointer or stride");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D % 128 == 0 && (D / 128 == 3 || D / 128 == 6 || D / 128 == 8 || D / 128 == 9)) {
+    dim3 rgrid((T + 4 * kLnWarpRows - 1) / (4 * kLnWarpRows), B);
+#define LNB_CASE(NV)                                                                                             \
+  case NV:                                                                                                       \
+    if (dh_dtype == DITB200_BF16)                                                                                \
+      ln_modulate_bwd_rows_kernel<NV, __nv_bfloat16><<<rgrid, 128, 0, st>>>(                                     \
+          reinterpret_cast<const __nv_bfloat16*>(dh), x, scale, mod_stride, stats, dx, accumulate, dshift, dscale, \
+          dmod_stride, T);                                                                                       \
+    else                                                                                                         \
+      ln_modulate_bwd_rows_kernel<NV, float><<<rgrid, 128, 0, st>>>(reinterpret_cast<const float*>(dh), x, scale, \
+                                                                   mod_stride, stats, dx, accumulate, dshift,    \
+                                                                   dscale, dmod_stride, T);                      \
+    break;
+    switch (D / 128) {
+      LNB_CASE(3)
+      LNB_CASE(6)
+      LNB_CASE(8)
+      LNB_CASE(9)
+    }
+#undef LNB_CASE
+    DITB_LAUNCH_CHECK("ln_modulate_bwd");
+    return 0;
+  }
   dim3 grid((T + kLnRows - 1) / kLnRows, B);
   const size_t smem = (size_t)2 * D * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
   if (dh_dtype == DITB200_BF16)
     ln_modulate_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(dh), x, scale,
                                                                   mod_stride, stats, dx, accumulate, dshift, dscale,
@@ -222,6 +336,8 @@ extern "C" int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_
   DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0 && B <= 65535, DITB200_EINVAL, "gate_resid_bwd: bad shape");
   DITB_REQUIRE(aligned16(dx_out) && aligned16(y) && aligned16(dy) && aligned16(gate) && gate_stride % 4 == 0,
                DITB200_EALIGN, "gate_resid_bwd: misaligned pointer or stride");
+  DITB_REQUIRE(aligned16(dgate) && dgate_stride % 4 == 0 && (!dbias || aligned16(dbias)), DITB200_EALIGN,
+               "gate_resid_bwd: dgate / dbias must be 16-byte aligned (128-bit reductions)");
   const int threads = 256;
   dim3 grid((T + kGrRows - 1) / kGrRows, B, (D / 4 + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
@@ -239,7 +355,7 @@ extern "C" int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_
 extern "C" int ditb200_colsum(const void* in, int dtype, float* out, int accumulate, int R, int C, void* stream) {
   DITB_REQUIRE(in && out, DITB200_EINVAL, "colsum: null pointer");
   DITB_REQUIRE(R > 0 && C > 0 && C % 4 == 0, DITB200_EINVAL, "colsum: bad shape R=%d C=%d (C %% 4 == 0)", R, C);
-  DITB_REQUIRE(aligned16(in), DITB200_EALIGN, "colsum: misaligned input");
+  DITB_REQUIRE(aligned16(in) && aligned16(out), DITB200_EALIGN, "colsum: misaligned input / output");
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) {
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st);

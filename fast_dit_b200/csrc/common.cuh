@@ -97,6 +97,36 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   return r;
 }
 
+// Pinned loads: `asm volatile` keeps them where they are written relative to the other volatile asm (TMEM
+// loads / waits), so a batch issued ahead of a wait stays a batch instead of being sunk to its first use.
+__device__ __forceinline__ float4 ldg_pinned_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_pinned_u2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+
+// 128-bit shared-memory accesses by 32-bit shared-window address.  Pointers derived from the manually aligned
+// dynamic-smem base lose their address space (the compiler emits generic LD/ST, which queue behind global
+// traffic on the long scoreboard); these stay LDS/STS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128_f(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint4 lds128_u(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -166,7 +166,7 @@ extern "C" int ditb200_gemm(const ditb200_gemm_args* a, void* stream) {
   DITB_REQUIRE(a->a && a->w && a->out, DITB200_EINVAL, "gemm: null tensor");
   DITB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, DITB200_EINVAL, "gemm: bad shape %d %d %d", a->M,
                a->N, a->K);
-  DITB_REQUIRE(a->epilogue >= 0 && a->epilogue <= DITB200_EPI_MUL_DGELU, DITB200_EINVAL,
+  DITB_REQUIRE(a->epilogue >= 0 && a->epilogue <= DITB200_EPI_MUL_AUX, DITB200_EINVAL,
                "gemm: bad epilogue %d", a->epilogue);
   DITB_REQUIRE(a->out_dtype == DITB200_F32 || a->out_dtype == DITB200_BF16, DITB200_EINVAL,
                "gemm: bad out_dtype");
@@ -179,7 +179,7 @@ extern "C" int ditb200_gemm(const ditb200_gemm_args* a, void* stream) {
   if (a->engine == DITB200_GEMM_TCGEN05) return launch_gemm_tcgen05(a, (cudaStream_t)stream);
   DITB_REQUIRE(a->engine == DITB200_GEMM_FP32, DITB200_EINVAL, "gemm: bad engine %d", a->engine);
   DITB_REQUIRE(!a->trans_a && !a->trans_w && !a->aux_out && !a->aux_in && !a->accumulate && a->split_k <= 1 &&
-                   a->epilogue != DITB200_EPI_MUL_DGELU,
+                   a->epilogue < DITB200_EPI_MUL_DGELU,
                DITB200_EINVAL, "gemm: the fp32 check engine runs the forward GEMMs only (no trans/aux/split_k)");
   SimtArgs p{};
   p.a = reinterpret_cast<const float*>(a->a), p.lda = a->K;

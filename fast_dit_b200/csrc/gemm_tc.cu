@@ -76,6 +76,16 @@ __device__ __forceinline__ float dgelu_tanh_f(float u) {
   return 0.5f * (1.0f + t) + 0.5f * u * (1.0f - t * t) * k0 * (1.0f + 3.0f * k1 * u2);
 }
 
+// gelu_tanh(u) and its derivative from one tanh evaluation
+__device__ __forceinline__ void gelu_and_dgelu(float u, float& g, float& d) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u2 = u * u;
+  const float t = tanh_approx(k0 * u * fmaf(k1, u2, 1.0f));
+  const float hp = 0.5f * (1.0f + t);
+  g = u * hp;
+  d = fmaf(0.5f * u * (1.0f - t * t), k0 * fmaf(3.0f * k1, u2, 1.0f), hp);
+}
+
 // ------------------------------------------------------------------------------ epilogue
 // One epilogue warp owns 32 accumulator rows (its TMEM lane quarter) x NCH 32-column chunks of the tile.
 // tcgen05.ld hands every thread one ROW (32 consecutive columns); storing that way would touch 32 different
@@ -87,7 +97,7 @@ __device__ __forceinline__ float dgelu_tanh_f(float u) {
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_ATOMIC = 2 };
 
 template <int EPI, int OUT, int AUX, int NCH>
-__device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t taddr0, uint8_t* stg, const int lane,
+__device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t taddr0, const uint32_t stg, const int lane,
                                          const int row0, const int colw, const int nch, const int M, const int N,
                                          const bool add_bias) {
   const int epi = EPI >= 0 ? EPI : ep.epilogue;
@@ -95,7 +105,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
   const bool aux = AUX >= 0 ? (AUX != 0) : (ep.aux_out != nullptr);
   const int sub = lane >> 3, grp = lane & 7;
   const int rows_valid = M - row0;  // rows [0, rows_valid) of this warp's 32 exist (may be <= 0 or >= 32)
-  uint8_t* my_row = stg + lane * 128;
+  const uint32_t my_row = stg + (uint32_t)lane * 128u;  // shared-window addresses
   const int swz_w = lane & 7;
   // adaLN gate: one [N] vector per image.  Fast path: all 32 rows belong to the same image.
   const float* gate_base = nullptr;
@@ -107,13 +117,14 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
     gate_base = ep.gate + (size_t)(rows_valid > 0 ? g_lo : 0) * ep.gate_stride;
   }
   float4 r4[8];  // residual values of the chunk, requested before the accumulators are waited for (GATE_RESID only)
+  uint2 u2[8];   // fc1 pre-activations of the chunk (MUL_DGELU only), same idea
   auto load_resid = [&](int c, float4 (&dst)[8]) {
     const int col = colw + c * 32 + grp * 4;
     const float* rp = ep.resid + (size_t)row0 * N + col;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + sub;
-      if (col < N && r < rows_valid) dst[i] = *reinterpret_cast<const float4*>(rp + (size_t)r * N);
+      if (col < N && r < rows_valid) dst[i] = ldg_pinned_f4(rp + (size_t)r * N);
     }
   };
 #pragma unroll 1
@@ -122,10 +133,19 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
     uint32_t v[32];
     tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
     if (epi == DITB200_EPI_BIAS_GATE_RESID) load_resid(c, r4);
+    if (epi == DITB200_EPI_MUL_DGELU || epi == DITB200_EPI_MUL_AUX) {
+      const int colp = colw + c * 32 + grp * 4;
+      const __nv_bfloat16* up = ep.aux_in + (size_t)row0 * N + colp;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub;
+        if (colp < N && r < rows_valid) u2[i] = ldg_pinned_u2(up + (size_t)r * N);
+      }
+    }
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 8; ++g)
-      *reinterpret_cast<uint4*>(my_row + ((g ^ swz_w) << 4)) = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      sts128(my_row + (uint32_t)((g ^ swz_w) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     __syncwarp();
     const int col = colw + c * 32 + grp * 4;
     if (col < N) {
@@ -134,19 +154,37 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
       float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (epi == DITB200_EPI_BIAS_GATE_RESID && gate_uniform) g4 = __ldg(reinterpret_cast<const float4*>(gate_base + col));
       const size_t off0 = (size_t)row0 * N + col;
+      float4 fr[8];  // all eight staged rows first: the shared loads overlap instead of one per row iteration
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub;
+        fr[i] = lds128_f(stg + (uint32_t)(r * 128 + ((grp ^ (r & 7)) << 4)));
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = i * 4 + sub;
         if (r < rows_valid) {
-          float4 f = *reinterpret_cast<const float4*>(stg + r * 128 + ((grp ^ (r & 7)) << 4));
+          float4 f = fr[i];
           f.x += b4.x, f.y += b4.y, f.z += b4.z, f.w += b4.w;
           const size_t off = off0 + (size_t)r * N;
-          if (aux) {  // the pre-activation / un-gated branch value, kept for backward
+          if (aux && epi != DITB200_EPI_BIAS_GELU_DAUX) {  // the pre-activation / un-gated branch value, kept for backward
             uint2 pk;
             pk.x = pack_bf16x2(f.x, f.y), pk.y = pack_bf16x2(f.z, f.w);
             *reinterpret_cast<uint2*>(ep.aux_out + off) = pk;
           }
-          if (epi == DITB200_EPI_BIAS_GELU) {
+          if (epi == DITB200_EPI_BIAS_GELU_DAUX) {
+            float4 d;
+            gelu_and_dgelu(f.x, f.x, d.x), gelu_and_dgelu(f.y, f.y, d.y);
+            gelu_and_dgelu(f.z, f.z, d.z), gelu_and_dgelu(f.w, f.w, d.w);
+            uint2 pk;
+            pk.x = pack_bf16x2(d.x, d.y), pk.y = pack_bf16x2(d.z, d.w);
+            *reinterpret_cast<uint2*>(ep.aux_out + off) = pk;
+          } else if (epi == DITB200_EPI_MUL_AUX) {
+            const uint2 pk = u2[i];
+            const float2 u0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
+            const float2 u1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
+            f.x *= u0.x, f.y *= u0.y, f.z *= u1.x, f.w *= u1.y;
+          } else if (epi == DITB200_EPI_BIAS_GELU) {
             f.x = gelu_tanh_fast(f.x), f.y = gelu_tanh_fast(f.y), f.z = gelu_tanh_fast(f.z), f.w = gelu_tanh_fast(f.w);
           } else if (epi == DITB200_EPI_BIAS_SILU) {
             f.x = silu_f(f.x), f.y = silu_f(f.y), f.z = silu_f(f.z), f.w = silu_f(f.w);
@@ -156,7 +194,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
             const float4 rr = r4[i];
             f.x = fmaf(g4.x, f.x, rr.x), f.y = fmaf(g4.y, f.y, rr.y), f.z = fmaf(g4.z, f.z, rr.z), f.w = fmaf(g4.w, f.w, rr.w);
           } else if (epi == DITB200_EPI_MUL_DGELU) {
-            const uint2 pk = *reinterpret_cast<const uint2*>(ep.aux_in + off);
+            const uint2 pk = u2[i];
             const float2 u0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
             const float2 u1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
             f.x *= dgelu_tanh_f(u0.x), f.y *= dgelu_tanh_f(u0.y), f.z *= dgelu_tanh_f(u1.x), f.w *= dgelu_tanh_f(u1.y);
@@ -404,7 +442,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ========================================================================= epilogue
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
-    uint8_t* stg = smem_epi + (warp - 2) * kEpiStageBytes;
+    const uint32_t stg = smem_u32(smem_epi) + (uint32_t)((warp - 2) * kEpiStageBytes);
     int iter = 0;
     for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
@@ -419,6 +457,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const float* rp = ep.resid + (size_t)(row0 + lane) * N + pc0;
           for (int c = 0; c < pn; ++c)
             if (pc0 + c * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c * 32));
+        }
+      }
+      if (ep.epilogue == DITB200_EPI_MUL_DGELU || ep.epilogue == DITB200_EPI_MUL_AUX) {  // same for the saved fc1 values (bf16: 64 columns per line)
+        const int chunks_ = (ncols + 31) >> 5, c0_ = (chunks_ + 1) >> 1;
+        const int pc0 = n_blk * BN + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
+        if (row0 + lane < M) {
+          const __nv_bfloat16* up = ep.aux_in + (size_t)(row0 + lane) * N + pc0;
+          for (int c = 0; c < pn; c += 2)
+            if (pc0 + c * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(up + c * 32));
         }
       }
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -444,6 +491,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 1); else EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 0);
       } else if (ep.epilogue == DITB200_EPI_MUL_DGELU && omode == OUT_BF16 && !has_aux) {
         EPI_CASE(DITB200_EPI_MUL_DGELU, OUT_BF16, 0);
+      } else if (ep.epilogue == DITB200_EPI_MUL_AUX && omode == OUT_BF16 && !has_aux) {
+        EPI_CASE(DITB200_EPI_MUL_AUX, OUT_BF16, 0);
+      } else if (ep.epilogue == DITB200_EPI_BIAS_GELU_DAUX && omode == OUT_BF16 && has_aux) {
+        EPI_CASE(DITB200_EPI_BIAS_GELU_DAUX, OUT_BF16, 1);
       } else {
         EPI_CASE(-1, -1, -1);  // rare combinations: everything decided at run time
       }
@@ -627,9 +678,11 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   if (a->epilogue == DITB200_EPI_BIAS_GATE_RESID)
     DITB_REQUIRE(aligned16(a->resid) && aligned16(a->gate) && a->gate_stride % 4 == 0,
                  DITB200_EALIGN, "gemm(tcgen05): resid/gate misaligned");
-  if (a->epilogue == DITB200_EPI_MUL_DGELU)
+  if (a->epilogue == DITB200_EPI_MUL_DGELU || a->epilogue == DITB200_EPI_MUL_AUX)
     DITB_REQUIRE(a->aux_in && aligned16(a->aux_in) && a->aux_dtype == DITB200_BF16, DITB200_EINVAL,
-                 "gemm(tcgen05): MUL_DGELU needs a 16-byte-aligned bf16 aux_in");
+                 "gemm(tcgen05): MUL_DGELU / MUL_AUX need a 16-byte-aligned bf16 aux_in");
+  if (a->epilogue == DITB200_EPI_BIAS_GELU_DAUX)
+    DITB_REQUIRE(a->aux_out != nullptr, DITB200_EINVAL, "gemm(tcgen05): BIAS_GELU_DAUX needs aux_out");
   if (a->aux_out)
     DITB_REQUIRE(aligned16(a->aux_out) && a->aux_dtype == DITB200_BF16, DITB200_EINVAL,
                  "gemm(tcgen05): aux_out must be 16-byte-aligned bf16");

@@ -56,13 +56,21 @@ class profile:
 
     def summary(self):
         out = {}
-        for name, e0, e1, meta in self.records:
+        for name, e0, e1, meta, _tag in self.records:
             n, ms, flops = out.get(name, (0, 0.0, 0.0))
             out[name] = (n + 1, ms + e0.elapsed_time(e1), flops + (meta or 0.0))
         return out
 
+    def summary_by_tag(self):
+        """{(kernel name, tag): (launches, total ms, flops)}; the GEMM tags itself with its shape and flags."""
+        out = {}
+        for name, e0, e1, meta, tag in self.records:
+            n, ms, flops = out.get((name, tag), (0, 0.0, 0.0))
+            out[(name, tag)] = (n + 1, ms + e0.elapsed_time(e1), flops + (meta or 0.0))
+        return out
 
-def _call(name, fn, *args, meta=None):
+
+def _call(name, fn, *args, meta=None, tag=None):
     """Invoke one C-ABI entry point (= one kernel launch) and check its return code."""
     global LAUNCHES
     LAUNCHES += 1
@@ -73,7 +81,7 @@ def _call(name, fn, *args, meta=None):
     e0.record()
     L.check(fn(*args), name)
     e1.record()
-    _PROFILE.append((name, e0, e1, meta))
+    _PROFILE.append((name, e0, e1, meta, tag))
 
 
 def _chk_contig(*ts):
@@ -175,7 +183,11 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
                       _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
                       int(trans_a), int(trans_w))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
-          meta=2.0 * M * N * K)
+          meta=2.0 * M * N * K,
+          tag=None if _PROFILE is None else
+          f"M{M} N{N} K{K} epi{epilogue}{' tA' if trans_a else ''}{' tW' if trans_w else ''}"
+          f"{' sk' + str(split_k) if split_k > 1 else ''}{' acc' if accumulate else ''}{' aux' if aux_out is not None else ''}"
+          f" {'f32' if out.dtype == torch.float32 else 'bf16'}")
     return out
 
 

@@ -205,7 +205,8 @@ class _DiTFunction(torch.autograd.Function):
             st2 = torch.empty((M, 2), device=dev, dtype=torch.float32)
             hB = ops.ln_modulate(x_mid, sh2, sc2, T, out_dtype=bf, stats=st2)
             a1 = torch.empty((M, w[4 * i + 2].shape[0]), device=dev, dtype=bf)
-            u = ops.gemm(hB, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU, aux_out=a1)
+            # a1 receives gelu'(fc1 pre-activation): the backward epilogue multiplies instead of re-evaluating tanh
+            u = ops.gemm(hB, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU_DAUX, aux_out=a1)
             y2 = torch.empty((M, D), device=dev, dtype=bf)
             x_out = torch.empty_like(tok)
             ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x_mid, gate=g2,
@@ -275,7 +276,7 @@ class _DiTFunction(torch.autograd.Function):
             gb = G(blk.mlp.fc2.bias).zero_()
             dy2 = ops.gate_resid_bwd(dtok, y2, g2, T, dm[5], dbias=gb)
             _wgrad(dy2, u, G(blk.mlp.fc2.weight))
-            da1 = _dgrad(dy2, w[4 * i + 3], epilogue=L.EPI_MUL_DGELU, aux_in=a1)
+            da1 = _dgrad(dy2, w[4 * i + 3], epilogue=L.EPI_MUL_AUX, aux_in=a1)
             _wgrad(da1, hB, G(blk.mlp.fc1.weight))
             ops.colsum(da1, out=G(blk.mlp.fc1.bias))
             dh = _dgrad(da1, w[4 * i + 2])

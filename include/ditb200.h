@@ -45,6 +45,10 @@ extern "C" {
 #define DITB200_EPI_BIAS_GATE_RESID 2 /* out_f32 = resid + gate[row/T] * (acc + bias)  */
 #define DITB200_EPI_BIAS_SILU 3       /* out = silu(acc + bias)                        */
 #define DITB200_EPI_MUL_DGELU 4       /* out = (acc + bias) * gelu_tanh'(aux_in)  (backward of fc1's GELU) */
+#define DITB200_EPI_BIAS_GELU_DAUX 5  /* out = gelu_tanh(acc + bias) and aux_out = gelu_tanh'(acc + bias): the forward
+                                         leaves the derivative behind, so the backward multiplies instead of
+                                         re-evaluating tanh in its epilogue */
+#define DITB200_EPI_MUL_AUX 6         /* out = (acc + bias) * aux_in  (fc2 data gradient times the saved gelu') */
 
 /* GEMM engines */
 #define DITB200_GEMM_TCGEN05 0 /* bf16 operands, tcgen05.mma + TMEM accumulators, TMA-fed */

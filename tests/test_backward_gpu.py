@@ -85,6 +85,16 @@ def test_gemm_aux_out_and_dgelu(ops, dev):
     F.gelu(pre, approximate="tanh").backward(dy.double() @ w2.double())
     got = ops.gemm(dy, w2, None, trans_w=True, epilogue=L.EPI_MUL_DGELU, aux_in=aux)
     assert rel_l2(got.float(), pre.grad) < 5e-3
+    # the pair the training step uses: forward leaves gelu'(pre) behind, backward multiplies by it
+    daux = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    u2 = ops.gemm(a, w, b, epilogue=L.EPI_BIAS_GELU_DAUX, aux_out=daux)
+    assert rel_l2(u2.float(), F.gelu(pre_ref, approximate="tanh")) < 4e-3
+    pre_d = pre_ref.clone().requires_grad_(True)
+    F.gelu(pre_d, approximate="tanh").sum().backward()
+    assert rel_l2(daux.float(), pre_d.grad) < 4e-3
+    got2 = ops.gemm(dy, w2, None, trans_w=True, epilogue=L.EPI_MUL_AUX, aux_in=daux)
+    assert rel_l2(got2.float(), (dy.double() @ w2.double()) * daux.double()) < 4e-3
+    assert rel_l2(got2.float(), (dy.double() @ w2.double()) * pre_d.grad) < 8e-3
 
 
 # ---------------------------------------------------------------------- elementwise backward

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--n", type=int, default=1152)
     ap.add_argument("--k", type=int, default=1152)
     ap.add_argument("--cfgs", default="0x0")
-    ap.add_argument("--epi", type=int, default=0, help="0 bias, 1 gelu, 2 gate+resid")
+    ap.add_argument("--epi", type=int, default=0, help="0 bias, 1 gelu, 2 gate+resid, 4 mul dgelu (bf16 aux_in)")
     ap.add_argument("--iters", type=int, default=40)
     ap.add_argument("--sets", type=int, default=4)
     ap.add_argument("--check", action="store_true")
@@ -47,6 +47,9 @@ def main():
                       out=res if a.inplace else torch.empty(M, N, device=dev))
         elif a.epi == 1:
             kw.update(epilogue=L.EPI_BIAS_GELU, out=torch.empty(M, N, device=dev, dtype=torch.bfloat16))
+        elif a.epi == 4:
+            kw.update(epilogue=L.EPI_MUL_DGELU, aux_in=torch.randn(M, N, device=dev, generator=g).bfloat16(),
+                      out=torch.empty(M, N, device=dev, dtype=torch.bfloat16))
         elif a.split_k > 1:
             kw.update(out=torch.empty(M, N, device=dev), out_dtype=torch.float32, split_k=a.split_k)
         else:
@@ -86,6 +89,10 @@ def main():
                 ref = Af @ Wf + kw["bias"]
                 if a.epi == 1:
                     ref = torch.nn.functional.gelu(ref, approximate="tanh")
+                if a.epi == 4:
+                    u = kw["aux_in"].float().requires_grad_(True)
+                    torch.nn.functional.gelu(u, approximate="tanh").sum().backward()
+                    ref = ref * u.grad
                 if a.epi == 2:
                     ref = res0 + kw["gate"].repeat_interleave(T, 0)[:M] * ref
                 err = float((got - ref).norm() / ref.norm())
