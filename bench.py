@@ -298,7 +298,7 @@ def run_ours(args):
     mfu = value / world * flops_img / 1e12 / tf_peak
 
     line = {
-        "metric": "DiT-XL/2 256px 250-step CFG-4.0 sampling throughput", "value": value, "unit": "img/s",
+        "metric": f"{name} {lat * 8}px {T}-step CFG-{CFG_SCALE} sampling throughput", "value": value, "unit": "img/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{name} {lat}x{lat}x4 latent, {T}-step DDPM sampling, CFG {CFG_SCALE}, "

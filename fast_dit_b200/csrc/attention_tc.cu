@@ -17,6 +17,8 @@
 // hd = 72 (DiT-XL) is handled without padding copies: the TMA tensor map is 3-D {hd, 3H heads, tokens}, the first
 // 64 channels land as a 128-byte-swizzled tile and channels 64..79 as a second, 32-byte-swizzled tile whose
 // columns >= hd are zero-filled by TMA (out of bounds in dimension 0); each gets its own tcgen05.mma.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ditb200 {
@@ -328,6 +330,315 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ============================================================================ long sequences (T > 256)
+// KV-blocked variant for T = 512, 768, 1024, ... (the 512 px configuration: 1024 tokens).  A work item is one
+// (image, head, PAIR of 128-query tiles); K and V stream through a 4-stage ring in blocks of 128 keys, each block
+// serving both query tiles.  Per query tile the score block S (128 x 128 f32) and the output accumulator O live
+// in TMEM side by side (128 + 80 columns), so the softmax is the online form:
+//   block max -> m_new, alpha = exp2((m_old - m_new) scale);  O *= alpha in TMEM (skipped when no row of the warp
+//   changed its maximum);  P = exp2((S - m_new) scale) -> TMEM over S;  l = l alpha + sum P;  O += P V_j.
+// tcgen05.mma instructions of one CTA execute in issue order, which is what orders  P_j's read by PV_j  before
+// S_{j+1} overwrites it, and PV_{j-1}'s write of O before the commit that publishes S_j: no extra barriers.
+// Issue order: S(0,0) S(1,0) | PV(0,g) S(0,g+1) PV(1,g) S(1,g+1) | ... over the flattened (item, block) sequence g.
+struct AttnKvSmem {
+  static constexpr int kQ0 = kAtQ * 128, kQ1 = kAtQ * 32;
+  static constexpr int kBlk = 128;                                   // keys per KV block
+  static constexpr int kK0 = kBlk * 128, kK1 = kBlk * 32, kV0 = kBlk * 128, kV1 = kBlk * 32;
+  static constexpr int kKV = kK0 + kK1 + kV0 + kV1;                  // 40 KB per stage
+  static constexpr int kStages = 4;
+  static constexpr int oQ0 = 0, oQ1 = oQ0 + 2 * kQ0, oKV = oQ1 + 2 * kQ1;
+  static constexpr int kStg = 32 * 64;
+  static constexpr int oStg = oKV + kStages * kKV;
+  static constexpr int oBars = oStg + 8 * kStg;
+  static constexpr int kBytes = oBars + 256 + 1024;
+};
+constexpr int kKvRegion = 256, kKvOCol = 128;  // TMEM: [S/P 128 | O 80 | spare] per query tile
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_v0,
+                      const __grid_constant__ CUtensorMap map_q1, __nv_bfloat16* __restrict__ out,
+                      float* __restrict__ lse, const int B, const int T, const int H, const int hd,
+                      const float scale_log2e) {
+  using SM = AttnKvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::oBars);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* kv_full = bars + 4;    // [4]
+  uint64_t* kv_empty = bars + 8;   // [4]
+  uint64_t* s_full = bars + 12;    // [2]
+  uint64_t* p_full = bars + 14;    // [2]  128 arrivals
+  uint64_t* o_full = bars + 16;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_c1 = hd > 64;
+  const int D = H * hd;
+  const int nblk = T / SM::kBlk;     // KV blocks per head
+  const int pairs = T / (2 * kAtQ);  // query-tile pairs per head
+  const int n_items = B * H * pairs;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_q0), tma_prefetch_desc(&map_v0), tma_prefetch_desc(&map_q1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1), mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1), mbar_init(&p_full[i], 128), mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < SM::kStages; ++i) mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    // ================================================================== TMA producer
+    const uint32_t q_bytes = (uint32_t)(SM::kQ0 + (has_c1 ? SM::kQ1 : 0));
+    const uint32_t kv_bytes = (uint32_t)(SM::kK0 + SM::kV0 + (has_c1 ? SM::kK1 + SM::kV1 : 0));
+    int it = 0, g = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int bh = w / pairs, pr = w - bh * pairs;
+      const int b = bh / H, h = bh - b * H;
+      const int tok0 = b * T;
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&q_empty[t], (uint32_t)(it & 1) ^ 1u);
+        if (elect_one()) {
+          const int q0 = tok0 + (2 * pr + t) * kAtQ;
+          mbar_arrive_expect_tx(&q_full[t], q_bytes);
+          tma_load_3d(&map_q0, &q_full[t], smem + SM::oQ0 + t * SM::kQ0, 0, h, q0);
+          if (has_c1) tma_load_3d(&map_q1, &q_full[t], smem + SM::oQ1 + t * SM::kQ1, 64, h, q0);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < nblk; ++j, ++g) {
+        const int stage = g % SM::kStages;
+        mbar_wait(&kv_empty[stage], (uint32_t)((g / SM::kStages) & 1) ^ 1u);
+        if (elect_one()) {
+          uint8_t* kv = smem + SM::oKV + stage * SM::kKV;
+          const int k0 = tok0 + j * SM::kBlk;
+          mbar_arrive_expect_tx(&kv_full[stage], kv_bytes);
+          tma_load_3d(&map_q0, &kv_full[stage], kv, 0, H + h, k0);  // K block: same {64 ch, 128 tokens} box as Q
+          if (has_c1) tma_load_3d(&map_q1, &kv_full[stage], kv + SM::kK0, 64, H + h, k0);
+          uint8_t* v0 = kv + SM::kK0 + SM::kK1;
+          tma_load_3d(&map_v0, &kv_full[stage], v0, 0, 2 * H + h, k0);
+          tma_load_3d(&map_v0, &kv_full[stage], v0 + 8192, 0, 2 * H + h, k0 + 64);
+          if (has_c1) tma_load_3d(&map_q1, &kv_full[stage], v0 + SM::kV0, 64, 2 * H + h, k0);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 9) {
+    // ==================================================================== MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(kAtQ, SM::kBlk);
+    const uint32_t idesc_o64 = umma_idesc_bf16(kAtQ, 64) | (1u << 16);
+    const uint32_t idesc_o16 = umma_idesc_bf16(kAtQ, 16) | (1u << 16);
+    int my_items = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) ++my_items;
+    const int G = my_items * nblk;  // (item, block) steps of this CTA
+    auto issue_s = [&](int t, int g) {
+      const int stage = g % SM::kStages, blk = g % nblk;
+      const uint32_t kv = smem_u32(smem + SM::oKV + stage * SM::kKV);
+      const uint32_t k0 = kv, k1 = kv + SM::kK0;
+      const uint32_t d = tmem_base + (uint32_t)(t * kKvRegion);
+      const uint32_t q0 = smem_u32(smem + SM::oQ0 + t * SM::kQ0), q1 = smem_u32(smem + SM::oQ1 + t * SM::kQ1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
+      if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
+      umma_commit<1>(&s_full[t]);
+      if (blk == nblk - 1) umma_commit<1>(&q_empty[t]);  // last score block of the item: Q tile may be refilled
+    };
+    auto issue_pv = [&](int t, int g) {
+      const int stage = g % SM::kStages, blk = g % nblk;
+      const uint32_t kv = smem_u32(smem + SM::oKV + stage * SM::kKV);
+      const uint32_t v0 = kv + SM::kK0 + SM::kK1, v1 = v0 + SM::kV0;
+      const uint32_t p = tmem_base + (uint32_t)(t * kKvRegion);
+      const uint32_t d = p + kKvOCol;
+#pragma unroll
+      for (int ks = 0; ks < SM::kBlk / 16; ++ks) {
+        const uint32_t acc = (blk > 0 || ks > 0) ? 1u : 0u;  // first block of an item overwrites O
+        umma_bf16_ts(d, p + 8 * ks, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, acc);
+        if (has_c1) umma_bf16_ts(d + 64, p + 8 * ks, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, acc);
+      }
+      if (blk == nblk - 1) umma_commit<1>(&o_full[t]);
+      if (t == 1) umma_commit<1>(&kv_empty[stage]);  // both query tiles are through with this K/V block
+    };
+    auto wait_inputs_s = [&](int t, int g) {  // K block g (and, for an item's first block, its Q tile)
+      if (t == 0) mbar_wait(&kv_full[g % SM::kStages], (uint32_t)((g / SM::kStages) & 1));
+      if (g % nblk == 0) mbar_wait(&q_full[t], (uint32_t)((g / nblk) & 1));
+    };
+    if (G > 0) {
+      for (int t = 0; t < 2; ++t) {
+        wait_inputs_s(t, 0);
+        tcgen05_fence_after();
+        if (elect_one()) issue_s(t, 0);
+        __syncwarp();
+      }
+    }
+    for (int g = 0; g < G; ++g) {
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_full[t], (uint32_t)(g & 1));
+        tcgen05_fence_after();
+        if (elect_one()) issue_pv(t, g);
+        __syncwarp();
+        if (g + 1 < G) {
+          wait_inputs_s(t, g + 1);
+          tcgen05_fence_after();
+          if (elect_one()) issue_s(t, g + 1);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // =================================================== online softmax + output, one thread per query row
+    const int t = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kKvRegion);
+    int it = 0, g = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int bh = w / pairs, pr = w - bh * pairs;
+      const int b = bh / H, h = bh - b * H;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nblk; ++j, ++g) {
+        mbar_wait(&s_full[t], (uint32_t)(g & 1));
+        tcgen05_fence_after();
+        uint32_t va[32], vb[32];
+        // ---- block maximum
+        float mx = m_run;
+        tmem_ld_32x32(trow, va);
+        tmem_ld_32x32(trow + 32, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[q]), __uint_as_float(va[q + 1])));
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[q]), __uint_as_float(vb[q + 1])));
+        tmem_ld_32x32(trow + 64, va);
+        tmem_ld_32x32(trow + 96, vb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[q]), __uint_as_float(va[q + 1])));
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[q]), __uint_as_float(vb[q + 1])));
+        // ---- rescale the running output when some row of this warp moved its maximum
+        const float alpha = ex2_approx((m_run - mx) * scale_log2e);  // first block: exp2(-inf) = 0
+        if (j > 0 && __any_sync(0xffffffffu, mx > m_run)) {
+          uint32_t o2[16];
+          tmem_ld_32x32(trow + kKvOCol, va);
+          tmem_ld_32x32(trow + kKvOCol + 32, vb);
+          if (has_c1) tmem_ld_32x16(trow + kKvOCol + 64, o2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) va[q] = __float_as_uint(__uint_as_float(va[q]) * alpha);
+#pragma unroll
+          for (int q = 0; q < 32; ++q) vb[q] = __float_as_uint(__uint_as_float(vb[q]) * alpha);
+          tmem_st_32x32(trow + kKvOCol, va);
+          tmem_st_32x32(trow + kKvOCol + 32, vb);
+          if (has_c1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) o2[q] = __float_as_uint(__uint_as_float(o2[q]) * alpha);
+            tmem_st_32x16(trow + kKvOCol + 64, o2);
+          }
+        }
+        l_run *= alpha;
+        m_run = mx;
+        // ---- P = exp2((S - m) scale), row sum, P -> TMEM (bf16, in place over S)
+        const float msc = mx * scale_log2e;
+        float sum0 = 0.f, sum1 = 0.f;
+        uint32_t pk[16];
+        tmem_ld_32x32(trow, va);
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          tmem_ld_wait();
+          tmem_ld_32x32(trow + 32 * (c + 1), vb);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * q]), scale_log2e, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * q + 1]), scale_log2e, -msc));
+            sum0 += p0, sum1 += p1;
+            pk[q] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(trow + 16 * c, pk);
+          tmem_ld_wait();
+          if (c + 2 < 4) tmem_ld_32x32(trow + 32 * (c + 2), va);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[2 * q]), scale_log2e, -msc));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[2 * q + 1]), scale_log2e, -msc));
+            sum0 += p0, sum1 += p1;
+            pk[q] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(trow + 16 * (c + 1), pk);
+        }
+        l_run += sum0 + sum1;
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(&p_full[t]);
+      }
+      // ---- output of this query tile: O / l -> bf16, staged for coalesced stores
+      mbar_wait(&o_full[t], (uint32_t)(it & 1));
+      tcgen05_fence_after();
+      uint32_t va[32], vb[32], o2[16];
+      tmem_ld_32x32(trow + kKvOCol, va);
+      tmem_ld_32x32(trow + kKvOCol + 32, vb);
+      if (has_c1) tmem_ld_32x16(trow + kKvOCol + 64, o2);
+      tmem_ld_wait();
+      const float inv = 1.0f / l_run;
+      const uint32_t stg = smem_u32(smem + SM::oStg) + (uint32_t)(warp * SM::kStg);
+      const int q_tile0 = (2 * pr + t) * kAtQ;
+      __nv_bfloat16* obase = out + ((size_t)b * T + q_tile0 + quarter * 32) * D + h * hd;
+      auto flush = [&](const uint32_t* v, int ncol, int col0) {
+        const uint32_t my = stg + (uint32_t)lane * 64u;
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          if (gq * 8 < ncol)
+            sts128(my + (uint32_t)((gq ^ sw) << 4),
+                   pack_bf16x2(__uint_as_float(v[8 * gq]) * inv, __uint_as_float(v[8 * gq + 1]) * inv),
+                   pack_bf16x2(__uint_as_float(v[8 * gq + 2]) * inv, __uint_as_float(v[8 * gq + 3]) * inv),
+                   pack_bf16x2(__uint_as_float(v[8 * gq + 4]) * inv, __uint_as_float(v[8 * gq + 5]) * inv),
+                   pack_bf16x2(__uint_as_float(v[8 * gq + 6]) * inv, __uint_as_float(v[8 * gq + 7]) * inv));
+        }
+        __syncwarp();
+        const int gq = lane & 3;
+        const int col = col0 + gq * 8;
+        if (gq * 8 < ncol && col < hd) {
+#pragma unroll
+          for (int pss = 0; pss < 4; ++pss) {
+            const int r = pss * 8 + (lane >> 2);
+            const uint4 q4 = lds128_u(stg + (uint32_t)(r * 64 + ((gq ^ ((r >> 1) & 3)) << 4)));
+            *reinterpret_cast<uint4*>(obase + (size_t)r * D + col) = q4;
+          }
+        }
+        __syncwarp();
+      };
+      flush(va, 32, 0);
+      flush(vb, 32, 32);
+      if (has_c1) flush(o2, 16, 64);
+      if (lse != nullptr)
+        lse[((size_t)b * H + h) * T + q_tile0 + row] = (m_run * scale_log2e + log2f(l_run)) * 0.6931471805599453f;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // 3-D bf16 tensor map over qkv viewed as {hd channels, 3H head slots, B*T tokens}
 static int make_tmap_qkv(CUtensorMap* map, const void* base, int hd, int H, uint64_t tokens, uint32_t box_ch,
                          uint32_t box_tok, CUtensorMapSwizzle swz) {
@@ -351,7 +662,9 @@ static int make_tmap_qkv(CUtensorMap* map, const void* base, int hd, int H, uint
   return 0;
 }
 
-bool attn_fwd_tc_supported(int T, int hd) { return (T == 128 || T == 256) && hd % 8 == 0 && hd >= 64 && hd <= 80; }
+bool attn_fwd_tc_supported(int T, int hd) {
+  return (T == 128 || T == 256 || (T > 256 && T % 256 == 0)) && hd % 8 == 0 && hd >= 64 && hd <= 80;
+}
 
 int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st) {
   DITB_REQUIRE(is_initialised(), DITB200_ENOINIT, "attention: ditb200_init() has not been called");
@@ -359,10 +672,29 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
   const uint64_t tokens = (uint64_t)B * T;
   int rc;
   if ((rc = make_tmap_qkv(&mq0, qkv, hd, H, tokens, 64, kAtQ, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_tmap_qkv(&mk0, qkv, hd, H, tokens, 64, (uint32_t)T, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  static const bool force_kv = getenv("DITB200_ATTN_KV") != nullptr;  // measurement switch: KV-blocked kernel at T = 256
+  const bool use_kv = T > 256 || (force_kv && T == 256);
+  const uint32_t kbox = use_kv ? (uint32_t)kAtQ : (uint32_t)T;  // the KV-blocked kernel loads K like Q (128 tokens)
+  if ((rc = make_tmap_qkv(&mk0, qkv, hd, H, tokens, 64, kbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_qkv(&mv0, qkv, hd, H, tokens, 64, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_qkv(&mq1, qkv, hd, H, tokens, 16, kAtQ, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_tmap_qkv(&mkv1, qkv, hd, H, tokens, 16, (uint32_t)T, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_tmap_qkv(&mkv1, qkv, hd, H, tokens, 16, kbox, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  const float scale_log2e = (float)(1.4426950408889634 / sqrt((double)hd));
+  if (use_kv) {  // KV-blocked online-softmax kernel
+    static bool kv_attr_set = false;
+    if (!kv_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           AttnKvSmem::kBytes);
+      if (e != cudaSuccess) return check_cuda(e, "attention_fwd(tcgen05, kv) smem attribute");
+      kv_attr_set = true;
+    }
+    int items = B * H * (T / 256), g = num_sms();
+    if (g > items) g = items;
+    attn_fwd_tc_kv_kernel<<<g, kAtThreads, AttnKvSmem::kBytes, st>>>(mq0, mv0, mq1, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                    lse, B, T, H, hd, scale_log2e);
+    DITB_LAUNCH_CHECK("attention_fwd(tcgen05, kv)");
+    return 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kBytes);
@@ -371,7 +703,6 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
   }
   int grid = num_sms();
   if (grid > B * H) grid = B * H;
-  const float scale_log2e = (float)(1.4426950408889634 / sqrt((double)hd));
   attn_fwd_tc_kernel<<<grid, kAtThreads, AttnSmem::kBytes, st>>>(mq0, mk0, mv0, mq1, mkv1,
                                                                  reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd,
                                                                  scale_log2e);

@@ -256,11 +256,13 @@ def test_attention_bf16(ops, dev, B, T, H, hd):
 
 
 @pytest.mark.parametrize("B,T,H,hd", [(1, 128, 1, 64), (3, 128, 5, 72), (20, 256, 16, 72), (40, 128, 12, 64),
-                                      (11, 256, 16, 80)])
+                                      (11, 256, 16, 80), (1, 512, 1, 64), (2, 768, 3, 72), (5, 1024, 16, 72),
+                                      (40, 512, 6, 64)])
 def test_attention_tcgen05_persistent(ops, dev, B, T, H, hd):
-    """The tcgen05/TMEM forward (T in {128, 256}): more (image, head) items than SMs, so every CTA runs
-    several items through its K/V ring and both barrier phases; hd 72/80 exercise the zero-filled second
-    channel chunk; scores scaled up so the row maximum matters."""
+    """The tcgen05/TMEM forward kernels (single score tile for T in {128, 256}; KV-blocked online softmax for
+    T = 512, 768, 1024): more work items than SMs, so every CTA runs several items through its K/V ring and
+    both barrier phases; hd 72/80 exercise the zero-filled second channel chunk; scores scaled up so the row
+    maximum (and the rescaling of the running output) matters."""
     g = torch.Generator(device=dev).manual_seed(18)
     qkv = (torch.randn(B * T, 3 * H * hd, device=dev, generator=g) * 2.0).bfloat16()
     lse = torch.empty(B, H, T, device=dev)
