@@ -138,7 +138,8 @@ def run_reference(args):
     sample = (f"{args.steps} timed CFG denoising steps of {name} at {n_ref} kept images (batch {2 * n_ref}), fp32, "
               f"{torch.get_num_threads()} threads; images/s = n / ({steps_total} steps x {dt:.3f} s/step), extrapolated")
     line = {
-        "impl": "reference", "metric": "DiT-XL/2 256px 250-step CFG-4.0 sampling throughput", "value": value,
+        "impl": "reference", "metric": f"{name} {lat * 8}px {steps_total}-step CFG-{CFG_SCALE} sampling throughput",
+        "value": value,
         "unit": "img/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name} {lat}x{lat}x4 latent, {steps_total}-step DDPM, CFG {CFG_SCALE}",
