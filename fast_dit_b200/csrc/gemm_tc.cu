@@ -25,6 +25,7 @@
 // Work units are (tile, k-split); tiles are visited n-fastest so the CTAs running at the same time
 // share A row-panels in L2.  With split_k > 1 partial tiles are combined with f32 vector atomics.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -35,7 +36,8 @@ constexpr int kBK = 64;        // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;     // K per tcgen05.mma for 16-bit inputs
 constexpr int kEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;
-constexpr int kEpiStageBytes = 32 * 128;                 // per epilogue warp: 32 rows x 32 f32 transpose buffer
+constexpr int kEpiStageBytes = 2 * 32 * 128;             // per epilogue warp: 32 rows x 32 f32 transpose buffer, or two
+                                                         // 32 x 64 bf16 TMA-store tiles
 constexpr int kSmemBudget = 232448 - 1024 - 256 - kEpiWarps * kEpiStageBytes;  // what is left for the TMA ring
 constexpr int kMnChunkBytes = 64 * kBK * 2;  // one {64 MN x 64 k} TMA box of an MN-major operand
 
@@ -49,6 +51,7 @@ struct EpiParams {
   int gate_stride, rows_per_gate;
   int epilogue, out_bf16;
   int atomic;  // out += (f32 vector atomics): split-K partials and gradient accumulation
+  int tma_store;  // bf16 output through smem staging + TMA store (tma_out is valid)
 };
 
 template <int kCG, int BN>
@@ -283,6 +286,65 @@ struct TileSched {
   }
 };
 
+// bf16 outputs without a second operand (bias / bias+GELU): the accumulator rows a thread gets from tcgen05.ld
+// are finished in place, packed, written to one of the warp's two 4 KB staging tiles in the 128-byte-swizzled
+// layout of the output tensor map, and a single elected lane hands the 32-row x 64-column tile to TMA: whole
+// 128-byte lines per row, no transposing read-back, no per-row address arithmetic, no LSU store wavefronts;
+// rows / columns past the matrix are clipped by the tensor map.  A staging tile is reused once the bulk group
+// that read it has drained (two in flight).
+template <int EPI, int NCH>
+__device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensorMap* tma_out, const uint32_t taddr0,
+                                             const uint32_t stg, const int lane, const int row0, const int colw,
+                                             const int nch, const int N, const bool add_bias, int& buf) {
+  const uint32_t my_off = (uint32_t)lane * 128u;
+  const int sw = lane & 7;
+#pragma unroll 1
+  for (int c = 0; c < NCH; c += 2) {  // 64 columns per store
+    const int col = colw + c * 32;
+    if (c >= nch || col >= N) break;  // warp-uniform
+    const uint32_t tile = stg + (uint32_t)buf * 4096u;
+    if (lane == 0) bulk_wait_group_read<1>();  // the store issued two rounds ago has read this staging tile
+    __syncwarp();
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int colh = col + hh * 32;
+      uint32_t v[32];
+      if (c + hh < nch && colh < N) {  // warp-uniform; a missing half lies past the matrix (the split above) and is clipped
+        tmem_ld_32x32(taddr0 + (uint32_t)((c + hh) * 32), v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (colh + j < N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + colh + j));
+              f[j] += b4.x, f[j + 1] += b4.y, f[j + 2] += b4.z, f[j + 3] += b4.w;
+            }
+          }
+        }
+        if (EPI == DITB200_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          sts128(tile + my_off + (uint32_t)(((hh * 4 + g) ^ sw) << 4), pack_bf16x2(f[8 * g], f[8 * g + 1]),
+                 pack_bf16x2(f[8 * g + 2], f[8 * g + 3]), pack_bf16x2(f[8 * g + 4], f[8 * g + 5]),
+                 pack_bf16x2(f[8 * g + 6], f[8 * g + 7]));
+      }
+    }
+    fence_proxy_async();  // make this thread's shared-memory writes visible to the async (TMA) proxy
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tma_out, tile, col, row0);
+      bulk_commit_group();
+    }
+    buf ^= 1;
+  }
+}
+
 // kMC = CTA pairs per cluster.  With kMC == 2 (cluster of 4 CTAs) the two pairs work on vertically adjacent
 // 256-row tiles of the same tile column and SHARE the B tile: every CTA fetches one quarter of it and TMA
 // multicasts that quarter to the CTA holding the same B half in the other pair, so a 512 x 256 super-tile moves
@@ -290,7 +352,7 @@ struct TileSched {
 template <int kCG, int BN, int kMC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
                const int split_k, const int part_cols) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
@@ -443,6 +505,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int quarter = warp & 3;         // TMEM lane quarter this warp may read
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
     const uint32_t stg = smem_u32(smem_epi) + (uint32_t)((warp - 2) * kEpiStageBytes);
+    int tma_buf = 0;
     int iter = 0;
     for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
@@ -472,7 +535,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       tcgen05_fence_after();
       const bool add_bias = ep.bias != nullptr && split == 0;
       // the tile's 32-column chunks are split between the two warps of the lane quarter (narrow tiles too)
-      const int chunks = (ncols + 31) >> 5, chunks0 = (chunks + 1) >> 1;
+      // (TMA-store path: 64-column stores, so the first warp takes an even number of chunks)
+      const int chunks = (ncols + 31) >> 5;
+      const int chunks0 = ep.tma_store ? min(chunks, (((chunks + 1) >> 1) + 1) & ~1) : (chunks + 1) >> 1;
       const int col_off = half ? chunks0 * 32 : 0;  // first tile column of this warp
       const int nch = half ? chunks - chunks0 : chunks0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_off);
@@ -481,7 +546,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #define EPI_CASE(E, O, A) epi_tile<E, O, A, NCH>(ep, taddr0, stg, lane, row0, colw, nch, M, N, add_bias)
       const bool has_aux = ep.aux_out != nullptr;
       const int omode = ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32);
-      if (ep.epilogue == DITB200_EPI_BIAS && !has_aux) {
+      if (ep.tma_store) {  // host: bf16 output, bias or bias+GELU, no aux tensor
+        if (ep.epilogue == DITB200_EPI_BIAS_GELU)
+          epi_tile_tma<DITB200_EPI_BIAS_GELU, NCH>(ep, &tma_out, taddr0, stg, lane, row0, colw, nch, N, add_bias, tma_buf);
+        else
+          epi_tile_tma<DITB200_EPI_BIAS, NCH>(ep, &tma_out, taddr0, stg, lane, row0, colw, nch, N, add_bias, tma_buf);
+      } else if (ep.epilogue == DITB200_EPI_BIAS && !has_aux) {
         if (omode == OUT_BF16) EPI_CASE(DITB200_EPI_BIAS, OUT_BF16, 0);
         else if (omode == OUT_F32) EPI_CASE(DITB200_EPI_BIAS, OUT_F32, 0);
         else EPI_CASE(DITB200_EPI_BIAS, OUT_ATOMIC, 0);
@@ -508,6 +578,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   }
 
+  if (warp >= 2 && lane == 0) bulk_wait_group_read<0>();  // staging tiles stay alive until TMA has read them
   tcgen05_fence_before();
   if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc<kCG>(tmem_base, Cfg::kTmemCols);
@@ -516,7 +587,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // ----------------------------------------------------------------------------- host side
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with a {box_rows x box_cols} box.
 static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                        uint32_t box_rows, uint32_t box_cols) {
+                        uint32_t box_rows, uint32_t box_cols, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) {
     set_error("gemm: ditb200_init() has not been called");
@@ -527,7 +598,7 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint6
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm: cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box=%ux%u)",
@@ -569,6 +640,17 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   ep.gate_stride = a->gate_stride, ep.rows_per_gate = a->rows_per_gate;
   ep.epilogue = a->epilogue, ep.out_bf16 = (a->out_dtype == DITB200_BF16);
   ep.atomic = (split_k > 1 || a->accumulate) ? 1 : 0;
+  CUtensorMap tout;
+  memset(&tout, 0, sizeof(tout));
+  static const bool no_tma_store = getenv("DITB200_NO_TMA_STORE") != nullptr;  // measurement switch
+  const bool tma_store = !no_tma_store && a->out_dtype == DITB200_BF16 && !a->aux_out && !a->aux_in &&
+                         (a->epilogue == DITB200_EPI_BIAS || a->epilogue == DITB200_EPI_BIAS_GELU) &&
+                         split_k == 1 && !a->accumulate;
+  if (tma_store) {
+    rc = make_tmap_2d(&tout, a->out, (uint64_t)a->M, (uint64_t)a->N, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  ep.tma_store = tma_store ? 1 : 0;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<kCG, BN, kMC>,
@@ -609,7 +691,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   if (clusters > units) clusters = units;
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, ep, a->M, a->N, a->K,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, ep, a->M, a->N, a->K,
                                      a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
