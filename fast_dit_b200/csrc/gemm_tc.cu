@@ -292,25 +292,42 @@ struct TileSched {
 // 128-byte lines per row, no transposing read-back, no per-row address arithmetic, no LSU store wavefronts;
 // rows / columns past the matrix are clipped by the tensor map.  A staging tile is reused once the bulk group
 // that read it has drained (two in flight).
-template <int EPI, int NCH>
-__device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensorMap* tma_out, const uint32_t taddr0,
+// MODE 0 bias, 1 bias+GELU, 2 bias+GELU' (second pass of GELU_DAUX over the same accumulators, into aux_out),
+// 3 (acc + bias) * aux_in with the aux_in tile fetched by TMA one round ahead.
+template <int MODE, int NCH>
+__device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensorMap* tma_st, const CUtensorMap* tma_ld,
+                                             uint64_t* ebar, uint32_t& ephase, const uint32_t taddr0,
                                              const uint32_t stg, const int lane, const int row0, const int colw,
                                              const int nch, const int N, const bool add_bias, int& buf) {
   const uint32_t my_off = (uint32_t)lane * 128u;
   const int sw = lane & 7;
+  if (MODE == 3) {  // tile 0 receives aux_in, tile 1 is the store source
+    if (lane == 0 && nch > 0 && colw < N) {
+      mbar_arrive_expect_tx(ebar, 32 * 128);
+      tma_load_2d(tma_ld, ebar, reinterpret_cast<void*>(__cvta_shared_to_generic((size_t)stg)), colw, row0);
+    }
+  }
 #pragma unroll 1
   for (int c = 0; c < NCH; c += 2) {  // 64 columns per store
     const int col = colw + c * 32;
     if (c >= nch || col >= N) break;  // warp-uniform
-    const uint32_t tile = stg + (uint32_t)buf * 4096u;
-    if (lane == 0) bulk_wait_group_read<1>();  // the store issued two rounds ago has read this staging tile
+    const uint32_t tile = MODE == 3 ? stg + 4096u : stg + (uint32_t)buf * 4096u;
+    if (lane == 0) {  // the store that last used this staging tile has read it
+      if (MODE == 3) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+    }
     __syncwarp();
+    if (MODE == 3) mbar_wait(ebar, ephase);
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
       const int colh = col + hh * 32;
       uint32_t v[32];
       if (c + hh < nch && colh < N) {  // warp-uniform; a missing half lies past the matrix (the split above) and is clipped
         tmem_ld_32x32(taddr0 + (uint32_t)((c + hh) * 32), v);
+        uint4 ax[4];
+        if (MODE == 3) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ax[g] = lds128_u(stg + my_off + (uint32_t)(((hh * 4 + g) ^ sw) << 4));
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -324,9 +341,25 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
             }
           }
         }
-        if (EPI == DITB200_EPI_BIAS_GELU) {
+        if (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
+        } else if (MODE == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float gdummy;
+            gelu_and_dgelu(f[j], gdummy, f[j]);
+          }
+        } else if (MODE == 3) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&ax[g]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 m = __bfloat1622float2(h2[q]);
+              f[8 * g + 2 * q] *= m.x, f[8 * g + 2 * q + 1] *= m.y;
+            }
+          }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -338,10 +371,14 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
     fence_proxy_async();  // make this thread's shared-memory writes visible to the async (TMA) proxy
     __syncwarp();
     if (lane == 0) {
-      tma_store_2d(tma_out, tile, col, row0);
+      tma_store_2d(tma_st, tile, col, row0);
       bulk_commit_group();
+      if (MODE == 3 && c + 2 < nch && col + 64 < N) {  // next round's aux_in tile (every lane has read this one)
+        mbar_arrive_expect_tx(ebar, 32 * 128);
+        tma_load_2d(tma_ld, ebar, reinterpret_cast<void*>(__cvta_shared_to_generic((size_t)stg)), col + 64, row0);
+      }
     }
-    buf ^= 1;
+    if (MODE == 3) ephase ^= 1u; else buf ^= 1;
   }
 }
 
@@ -352,7 +389,8 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
 template <int kCG, int BN, int kMC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
+               const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
                const int split_k, const int part_cols) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
@@ -368,6 +406,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_bar = bars + 2 * kStages + 5;  // [kEpiWarps] aux_in tiles landing in the epilogue staging (MUL_AUX)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cl_rank = (kCG == 2) ? cluster_ctarank() : 0u;  // rank in the cluster: pair = rank / 2
@@ -383,6 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&full[s], 1);    // one arrive.expect_tx (leader CTA) covering every CTA's bytes
       mbar_init(&empty[s], kMC);  // one tcgen05.commit per phase from every pair that reads (a copy of) the slot
     }
+    for (int s = 0; s < kEpiWarps; ++s) mbar_init(&epi_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCG);  // one arrive per epilogue warp of every CTA
@@ -506,6 +546,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int half = (warp - 2) >> 2;     // which half of the tile's columns
     const uint32_t stg = smem_u32(smem_epi) + (uint32_t)((warp - 2) * kEpiStageBytes);
     int tma_buf = 0;
+    uint32_t ephase = 0;
+    uint64_t* ebar = &epi_bar[warp - 2];
     int iter = 0;
     for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
@@ -546,11 +588,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #define EPI_CASE(E, O, A) epi_tile<E, O, A, NCH>(ep, taddr0, stg, lane, row0, colw, nch, M, N, add_bias)
       const bool has_aux = ep.aux_out != nullptr;
       const int omode = ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32);
-      if (ep.tma_store) {  // host: bf16 output, bias or bias+GELU, no aux tensor
-        if (ep.epilogue == DITB200_EPI_BIAS_GELU)
-          epi_tile_tma<DITB200_EPI_BIAS_GELU, NCH>(ep, &tma_out, taddr0, stg, lane, row0, colw, nch, N, add_bias, tma_buf);
-        else
-          epi_tile_tma<DITB200_EPI_BIAS, NCH>(ep, &tma_out, taddr0, stg, lane, row0, colw, nch, N, add_bias, tma_buf);
+#define EPI_TMA(MODE, ST) \
+  epi_tile_tma<MODE, NCH>(ep, ST, &tma_aux, ebar, ephase, taddr0, stg, lane, row0, colw, nch, N, add_bias, tma_buf)
+      if (ep.tma_store) {  // host: bf16 outputs finished in the accumulator's row layout and stored by TMA
+        if (ep.epilogue == DITB200_EPI_BIAS_GELU) EPI_TMA(1, &tma_out);
+        else if (ep.epilogue == DITB200_EPI_BIAS_GELU_DAUX) {
+          EPI_TMA(1, &tma_out);   // out = gelu(acc + bias)
+          EPI_TMA(2, &tma_aux);   // aux_out = gelu'(acc + bias), second pass over the same TMEM stage
+        } else if (ep.epilogue == DITB200_EPI_MUL_AUX) EPI_TMA(3, &tma_out);
+        else EPI_TMA(0, &tma_out);
       } else if (ep.epilogue == DITB200_EPI_BIAS && !has_aux) {
         if (omode == OUT_BF16) EPI_CASE(DITB200_EPI_BIAS, OUT_BF16, 0);
         else if (omode == OUT_F32) EPI_CASE(DITB200_EPI_BIAS, OUT_F32, 0);
@@ -569,6 +615,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         EPI_CASE(-1, -1, -1);  // rare combinations: everything decided at run time
       }
 #undef EPI_CASE
+#undef EPI_TMA
       // all tcgen05.ld of this stage are complete (wait::ld above): give the stage back
       tcgen05_fence_before();
       __syncwarp();
@@ -643,12 +690,23 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   CUtensorMap tout;
   memset(&tout, 0, sizeof(tout));
   static const bool no_tma_store = getenv("DITB200_NO_TMA_STORE") != nullptr;  // measurement switch
-  const bool tma_store = !no_tma_store && a->out_dtype == DITB200_BF16 && !a->aux_out && !a->aux_in &&
-                         (a->epilogue == DITB200_EPI_BIAS || a->epilogue == DITB200_EPI_BIAS_GELU) &&
+  CUtensorMap taux;
+  memset(&taux, 0, sizeof(taux));
+  const bool plain_bf16 = (a->epilogue == DITB200_EPI_BIAS || a->epilogue == DITB200_EPI_BIAS_GELU) && !a->aux_out && !a->aux_in;
+  const bool daux = a->epilogue == DITB200_EPI_BIAS_GELU_DAUX && a->aux_out && a->aux_dtype == DITB200_BF16;
+  const bool mulaux = a->epilogue == DITB200_EPI_MUL_AUX && a->aux_in && !a->aux_out;
+  // (a TMA load + store version of the f32 gated residual was measured 15 % slower than the register path: with
+  // 8 KB of staging per warp only one residual tile can be in flight ahead of the one being combined)
+  const bool tma_store = !no_tma_store && a->out_dtype == DITB200_BF16 && (plain_bf16 || daux || mulaux) &&
                          split_k == 1 && !a->accumulate;
   if (tma_store) {
     rc = make_tmap_2d(&tout, a->out, (uint64_t)a->M, (uint64_t)a->N, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+    if (daux || mulaux) {
+      rc = make_tmap_2d(&taux, daux ? a->aux_out : a->aux_in, (uint64_t)a->M, (uint64_t)a->N, 32, 64,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
   }
   ep.tma_store = tma_store ? 1 : 0;
   static bool attr_set = false;  // per instantiation; benign race (idempotent)
@@ -691,7 +749,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   if (clusters > units) clusters = units;
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, ep, a->M, a->N, a->K,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, taux, ep, a->M, a->N, a->K,
                                      a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
