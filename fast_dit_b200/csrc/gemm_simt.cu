@@ -126,7 +126,70 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const SimtArgs p) {
   }
 }
 
+// Small-M variant (M <= 64: the timestep MLP, adaLN in the fp32 check mode): the 64 x 64 tiling above leaves
+// N / 64 CTAs on a 148-SM machine.  Here a warp owns ONE output column for all M rows (lane = rows l, l + 32),
+// a CTA of 8 warps owns 8 columns, and A is staged through shared memory in 128-wide k slabs (row stride 129:
+// conflict-free column reads).  f32 FMAs in the same k order as above (partials flushed every 32 k).
+constexpr int kSmK = 128;
+__global__ void __launch_bounds__(256) gemm_simt_small_m_kernel(const SimtArgs p) {
+  __shared__ float As[64][kSmK + 1];
+  __shared__ float Ws[8][kSmK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += kSmK) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 64 * kSmK; idx += 256) {
+      const int r = idx / kSmK, k = idx - r * kSmK;
+      float v = 0.f;
+      if (r < p.M && k0 + k < p.K) {
+        v = p.a[(size_t)r * p.lda + k0 + k];
+        if (p.silu_in) v = silu_acc(v);
+      }
+      As[r][k] = v;
+    }
+    for (int idx = threadIdx.x; idx < 8 * kSmK; idx += 256) {
+      const int c = idx / kSmK, k = idx - c * kSmK;
+      const int nn = blockIdx.x * 8 + c;
+      Ws[c][k] = (nn < p.N && k0 + k < p.K) ? load_w(p.w, p.w_bf16, (size_t)nn * p.K + k0 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kc = 0; kc < kSmK; kc += 32) {
+      float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) {
+        const float wv = Ws[warp][kc + kk];
+        p0 = fmaf(As[lane][kc + kk], wv, p0);
+        p1 = fmaf(As[lane + 32][kc + kk], wv, p1);
+      }
+      acc0 += p0, acc1 += p1;
+    }
+  }
+  if (n >= p.N) return;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = lane + 32 * h;
+    if (m >= p.M) continue;
+    float v = h ? acc1 : acc0;
+    if (p.bias) v += p.bias[n];
+    if (p.epilogue == DITB200_EPI_BIAS_GELU) v = gelu_tanh_f(v);
+    else if (p.epilogue == DITB200_EPI_BIAS_SILU) v = silu_acc(v);
+    else if (p.epilogue == DITB200_EPI_BIAS_GATE_RESID)
+      v = p.resid[(size_t)m * p.ldo + n] + p.gate[(size_t)(m / p.rows_per_gate) * p.gate_stride + n] * v;
+    if (p.add) v += p.add[(size_t)m * p.ldadd + n];
+    if (p.out_bf16) p.out_bf16[(size_t)m * p.ldo + n] = __float2bfloat16_rn(v);
+    else p.out_f32[(size_t)m * p.ldo + n] = v;
+  }
+}
+
 int launch_gemm_simt(const SimtArgs& p, cudaStream_t st) {
+  if (p.M <= 64) {
+    gemm_simt_small_m_kernel<<<(p.N + 7) / 8, 256, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return check_cuda(e, "gemm_simt(small M)");
+    return 0;
+  }
   dim3 grid((p.N + kTN - 1) / kTN, (p.M + kTM - 1) / kTM);
   gemm_simt_kernel<<<grid, 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
