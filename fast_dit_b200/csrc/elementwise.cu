@@ -498,6 +498,99 @@ extern "C" int ditb200_silu_cast(const float* in, void* out, int out_dtype, size
   return 0;
 }
 
+// ---- 32-output variant (p = 2, learn_sigma: p*p*2C = 32; every */2 model): persistent, warp per token row.
+// The [32, D] weight lives in shared memory for the lifetime of the CTA; a warp holds its row in registers
+// (read once, the next row already in flight), normalises and modulates it there, forms 32 partial dot
+// products per lane and reduces the 32 x 32 partials with a 31-shuffle transpose-reduction, after which lane o
+// owns output o and stores it straight into its NCHW position (unpatchify).
+template <int NV>
+__global__ void __launch_bounds__(256) final_layer_rows_kernel(
+    const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ out, int M, int T, int p, int Cout, float eps, int round_bf16) {
+  constexpr int D = NV * 128;
+  extern __shared__ float ws[];  // [32][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 32 * D / 4; i += blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(w) + i);
+    if (round_bf16) v.x = bf16_round(v.x), v.y = bf16_round(v.y), v.z = bf16_round(v.z), v.w = bf16_round(v.w);
+    reinterpret_cast<float4*>(ws)[i] = v;
+  }
+  __syncthreads();
+  const int W = gridDim.x * 8;
+  int row = blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  const int Wp = (int)(sqrtf((float)T) + 0.5f), Himg = Wp * p;
+  const float b_o = bias[lane];
+  float4 v[NV], nx[NV];
+  {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = ldg_stream_f4(xr + lane + 32 * j);
+  }
+  for (; row < M; row += W) {
+    if (row + W < M) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(row + W) * D);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) nx[j] = ldg_stream_f4(xr + lane + 32 * j);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const int b = row / T, t = row - b * T;
+    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 h4 = __ldg(sh + lane + 32 * j), c4 = __ldg(sc + lane + 32 * j);
+      v[j].x = (v[j].x - mean) * rstd * (1.0f + c4.x) + h4.x;
+      v[j].y = (v[j].y - mean) * rstd * (1.0f + c4.y) + h4.y;
+      v[j].z = (v[j].z - mean) * rstd * (1.0f + c4.z) + h4.z;
+      v[j].w = (v[j].w - mean) * rstd * (1.0f + c4.w) + h4.w;
+      if (round_bf16)
+        v[j].x = bf16_round(v[j].x), v[j].y = bf16_round(v[j].y), v[j].z = bf16_round(v[j].z), v[j].w = bf16_round(v[j].w);
+    }
+    float acc[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)o * D);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 w4 = wr[lane + 32 * j];
+        a = fmaf(v[j].x, w4.x, a), a = fmaf(v[j].y, w4.y, a), a = fmaf(v[j].z, w4.z, a), a = fmaf(v[j].w, w4.w, a);
+      }
+      acc[o] = a;
+    }
+    // transpose-reduce: after the step with distance s, entry i of a lane holds the sum over its 32/s-lane group of
+    // output (i + the bits of `lane` already consumed); 16 + 8 + 4 + 2 + 1 shuffles leave output `lane` in acc[0]
+#pragma unroll
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+      const bool up = (lane & s2) != 0;
+#pragma unroll
+      for (int i = 0; i < s2; ++i) {
+        const float keep = up ? acc[i + s2] : acc[i];
+        const float send = up ? acc[i] : acc[i + s2];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+      }
+    }
+    // output o = lane: (pi, pj, c) = unpatchify order (models_original.py:228-230)
+    const int c = lane % Cout, pq = lane / Cout, pi = pq / p, pj = pq - pi * p;
+    const int hh = t / Wp, ww = t - hh * Wp;
+    out[(((size_t)b * Cout + c) * Himg + hh * p + pi) * Himg + ww * p + pj] = acc[0] + b_o;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = nx[j];
+  }
+}
+
 extern "C" int ditb200_final_layer(const float* x, const float* shift, const float* scale,
                                    int mod_stride, const float* w, const float* bias, float* out,
                                    int B, int T, int D, int p, int Cout, float eps, int round_bf16,
@@ -515,6 +608,28 @@ extern "C" int ditb200_final_layer(const float* x, const float* shift, const flo
   const int M = B * T;
   const dim3 grid((M + kFlRows - 1) / kFlRows), block(256);
   cudaStream_t st = (cudaStream_t)stream;
+  if (NO == 32 && D % 128 == 0 && aligned16(w) && (D / 128 == 3 || D / 128 == 6 || D / 128 == 8 || D / 128 == 9)) {
+    const size_t smem = (size_t)32 * D * sizeof(float);
+    int g = num_sms() > 0 ? num_sms() : 148;
+    if (g > (M + 7) / 8) g = (M + 7) / 8;
+#define FLR_CASE(NV)                                                                                           \
+  case NV: {                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(final_layer_rows_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                           \
+    if (e != cudaSuccess) return check_cuda(e, "final_layer smem attr");                                       \
+    final_layer_rows_kernel<NV><<<g, 256, smem, st>>>(x, shift, scale, mod_stride, w, bias, out, M, T, p, Cout, eps, \
+                                                      round_bf16);                                             \
+  } break;
+    switch (D / 128) {
+      FLR_CASE(3)
+      FLR_CASE(6)
+      FLR_CASE(8)
+      FLR_CASE(9)
+    }
+#undef FLR_CASE
+    DITB_LAUNCH_CHECK("final_layer");
+    return 0;
+  }
 #define FL_LAUNCH(NOW)                                                                          \
   {                                                                                             \
     const size_t smem = ((size_t)kFlRows * D + (size_t)(kFlKc + 4) * NOW * 32) * sizeof(float);       \
