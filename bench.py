@@ -291,7 +291,13 @@ def run_ours(args):
     achieved = g_flops / (g_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16, all DiT-block GEMMs + adaLN)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                "peak_source": which, "traffic": None, "launches_per_step": g_n // 3,
+                "peak_source": which,
+                # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest GEMM of the
+                # block (fc1, M=16384 N=4608 K=1152: 48.5 + 98.1 MB; algorithmic A + W + out = 199 MB, the rest stays
+                # in the 126 MB L2) -- profiles/r01_gemm_fc1_tma_full.md.  Tensor-bound kernel: context, not the bound.
+                "traffic": 146.6e6 if args.workload == "c3" else None,
+                "traffic_unit": "bytes per fc1 launch (ncu, profiles/r01_gemm_fc1_tma_full.md)",
+                "launches_per_step": g_n // 3,
                 "avg_launch_us": g_ms / g_n * 1e3, "share_of_step": g_ms / 3 / step_ms_events}
     breakdown = {k: {"launches": v[0] // 3, "ms": v[1] / 3} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
 

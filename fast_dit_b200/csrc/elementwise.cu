@@ -2,6 +2,8 @@
 // final layer, bf16 casts.  Each is bounded by the HBM roofline; the
 // rules that matter are coalesced 128-bit accesses, one pass over the data, and enough
 // CTAs to cover 148 SMs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ditb200 {
@@ -393,7 +395,11 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
                "ln_modulate: bad out_dtype %d", out_dtype);
   cudaStream_t st = (cudaStream_t)stream;
   const int M = B * T;
-  const dim3 grid((M + 7) / 8), block(256);
+  static const int ln_threads = getenv("DITB200_LN_THREADS") ? atoi(getenv("DITB200_LN_THREADS")) : 128;  // tuning switch (64..512)
+  DITB_REQUIRE(ln_threads >= 32 && ln_threads <= 256 && ln_threads % 32 == 0, DITB200_EINVAL,
+               "ln_modulate: DITB200_LN_THREADS must be a multiple of 32 in [32, 256]");
+  const int wpb = ln_threads / 32;
+  const dim3 grid((M + wpb - 1) / wpb), block(ln_threads);
   const bool bf = out_dtype == DITB200_BF16;
 #define LN_CASE(NV)                                                                              \
   case NV * 128:                                                                                 \
