@@ -649,6 +649,9 @@ namespace ditb200 {
 // attention_tc.cu: tcgen05 / TMEM forward for T in {128, 256}, head dim 64..80
 bool attn_fwd_tc_supported(int T, int hd);
 int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+bool attn_bwd_tc_supported(int T, int hd);
+int launch_attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv, int B, int T,
+                       int H, int hd, cudaStream_t st);
 }  // namespace ditb200
 
 extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
@@ -697,6 +700,8 @@ static int launch_attn_bwd_bf16(const void* qkv, const void* out, const void* do
   const int n = B * T * H;
   attn_bwd_dsum_kernel<HD><<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out), d_o, dsum, B, T, H);
   DITB_LAUNCH_CHECK("attention_bwd(dsum)");
+  static const bool legacy = getenv("DITB200_ATTN_MMA_SYNC") != nullptr;  // measurement switch
+  if (!legacy && attn_bwd_tc_supported(T, HD)) return launch_attn_bwd_tc(qkv, dout, lse, dsum, dqkv, B, T, H, HD, st);
   dim3 grid((T + 63) / 64, H, B);
   attn_bwd_dkv_kernel<HD><<<grid, 128, kSmem, st>>>(q, d_o, lse, dsum, dq, T, H, scale, scale_log2e);
   DITB_LAUNCH_CHECK("attention_bwd(dkv)");

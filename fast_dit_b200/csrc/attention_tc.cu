@@ -639,6 +639,266 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ================================================================================ backward (T = 256)
+// dQ, dK, dV of one (image, head) per work item, on the tensor cores, in four jobs that share the Q, K, V, dO
+// tiles held in shared memory (each [256 tokens x hd], loaded once by TMA; the same bytes serve as a K-major
+// operand "rows x channels" and as an MN-major operand "channels x tokens", only the descriptors differ):
+//   key tile kt (2 jobs):   S^T = K_kt Q^T,  dP^T = V_kt dO^T          (128 keys x 256 queries each, TMEM)
+//                           P^T = exp2(S^T s - lse[q]),  dS^T = P^T (dP^T - dsum[q]) scale      -> bf16 in TMEM
+//                           dV_kt = P^T dO,  dK_kt = dS^T Q                                     (A operand from TMEM)
+//   query tile qt (2 jobs): S = Q_qt K^T,  dP = dO_qt V^T;  dS = P (dP - dsum) scale;  dQ_qt = dS K
+// TMEM: columns [0,256) hold S / S^T, [256,512) dP / dP^T.  The 256 score columns of a job are produced and
+// consumed as two halves (warps 0-3 take columns [0,128), warps 4-7 [128,256)), so the second half's MMAs run
+// while the first half is exponentiated.  P / dS overwrite the first 64 columns of their own half; when both
+// halves are done the four 64-column holes left over take the output accumulators (channels 0..63 and 64..79 are
+// separate MMAs anyway), then the epilogue drains them and the next job starts.
+struct AttnBwdSmem {
+  static constexpr int kT = 256;
+  static constexpr int kC0 = kT * 128, kC1 = kT * 32;              // channel chunks 0..63 / 64..79 of one tensor
+  static constexpr int oQ0 = 0, oQ1 = oQ0 + kC0, oK0 = oQ1 + kC1, oK1 = oK0 + kC0, oV0 = oK1 + kC1, oV1 = oV0 + kC0,
+                       oD0 = oV1 + kC1, oD1 = oD0 + kC0;
+  static constexpr int oRow = oD1 + kC1;                             // lse*log2e [256], dsum [256]
+  static constexpr int kStg = 32 * 64;
+  static constexpr int oStg = oRow + 2 * kT * 4;
+  static constexpr int oBars = oStg + 8 * kStg;
+  static constexpr int kBytes = oBars + 128 + 1024;
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_constant__ CUtensorMap map_qkv1,
+                   const __grid_constant__ CUtensorMap map_do0, const __grid_constant__ CUtensorMap map_do1,
+                   const float* __restrict__ lse, const float* __restrict__ dsum, __nv_bfloat16* __restrict__ dqkv,
+                   const int B, const int H, const int hd, const float scale, const float scale_log2e) {
+  using SM = AttnBwdSmem;
+  constexpr int T = SM::kT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::oBars);
+  uint64_t* ld_full = bars;       // TMA -> MMA (item)
+  uint64_t* ld_empty = bars + 1;  // MMA -> TMA
+  uint64_t* s_full = bars + 2;    // [2] MMA -> elementwise, per column half
+  uint64_t* p_full = bars + 4;    // elementwise -> MMA (256 arrivals)
+  uint64_t* o_full = bars + 5;    // MMA -> epilogue
+  uint64_t* o_free = bars + 6;    // epilogue -> MMA (256 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  float* row_l2 = reinterpret_cast<float*>(smem + SM::oRow);
+  float* row_ds = row_l2 + T;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_c1 = hd > 64;
+  const int D = H * hd;
+  const int n_items = B * H;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_qkv0), tma_prefetch_desc(&map_qkv1), tma_prefetch_desc(&map_do0), tma_prefetch_desc(&map_do1);
+    mbar_init(ld_full, 1), mbar_init(ld_empty, 1), mbar_init(&s_full[0], 1), mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 256), mbar_init(o_full, 1), mbar_init(o_free, 256);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc<1>(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t RA = tmem_base, RB = tmem_base + 256;  // S / dP regions
+
+  if (warp == 8) {
+    // ================================================================== TMA producer
+    const uint32_t bytes = (uint32_t)(4 * SM::kC0 + (has_c1 ? 4 * SM::kC1 : 0));
+    int it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int b = w / H, h = w - b * H;
+      const int tok0 = b * T;
+      mbar_wait(ld_empty, (uint32_t)(it & 1) ^ 1u);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(ld_full, bytes);
+        tma_load_3d(&map_qkv0, ld_full, smem + SM::oK0, 0, H + h, tok0);
+        tma_load_3d(&map_qkv0, ld_full, smem + SM::oQ0, 0, h, tok0);
+        tma_load_3d(&map_qkv0, ld_full, smem + SM::oV0, 0, 2 * H + h, tok0);
+        tma_load_3d(&map_do0, ld_full, smem + SM::oD0, 0, h, tok0);
+        if (has_c1) {
+          tma_load_3d(&map_qkv1, ld_full, smem + SM::oK1, 64, H + h, tok0);
+          tma_load_3d(&map_qkv1, ld_full, smem + SM::oQ1, 64, h, tok0);
+          tma_load_3d(&map_qkv1, ld_full, smem + SM::oV1, 64, 2 * H + h, tok0);
+          tma_load_3d(&map_do1, ld_full, smem + SM::oD1, 64, h, tok0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    // ==================================================================== MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(kAtQ, 128);                   // scores: 128 x 128 per half, K-major both
+    const uint32_t idesc_o64 = umma_idesc_bf16(kAtQ, 64) | (1u << 16);     // outputs: B MN-major
+    const uint32_t idesc_o16 = umma_idesc_bf16(kAtQ, 16) | (1u << 16);
+    const uint32_t sQ0 = smem_u32(smem + SM::oQ0), sQ1 = smem_u32(smem + SM::oQ1);
+    const uint32_t sK0 = smem_u32(smem + SM::oK0), sK1 = smem_u32(smem + SM::oK1);
+    const uint32_t sV0 = smem_u32(smem + SM::oV0), sV1 = smem_u32(smem + SM::oV1);
+    const uint32_t sD0 = smem_u32(smem + SM::oD0), sD1 = smem_u32(smem + SM::oD1);
+    // D[128 x 128] = A_tile(rows at +tile*128) . B_half(rows at +half*128)^T over hd channels
+    auto scores = [&](uint32_t d, uint32_t a0, uint32_t a1, int tile, uint32_t b0, uint32_t b1, int half) {
+      const uint32_t ao0 = a0 + (uint32_t)tile * 16384u, ao1 = a1 + (uint32_t)tile * 4096u;
+      const uint32_t bo0 = b0 + (uint32_t)half * 16384u, bo1 = b1 + (uint32_t)half * 4096u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        umma_bf16<1>(d, mk_desc(kDescHiSw128, ao0 + 32 * j, 0), mk_desc(kDescHiSw128, bo0 + 32 * j, 0), idesc_s, j > 0);
+      if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, ao1, 1), mk_desc(kDescHiSw32, bo1, 1), idesc_s, 1u);
+    };
+    // D[128 x hd] = A[tmem, 128 x 256 packed bf16 in two 64-column pieces] . Bmn (channels x 256 tokens)
+    auto outputs = [&](uint32_t region, uint32_t b0, uint32_t b1) {
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks) {
+        const uint32_t a = region + (uint32_t)(ks < 8 ? 8 * ks : 128 + 8 * (ks - 8));
+        umma_bf16_ts(region + 64, a, mk_desc(kDescHiSw128, b0 + 2048 * ks, 0), idesc_o64, ks > 0);
+        if (has_c1) umma_bf16_ts(region + 192, a, mk_desc(kDescHiSw32, b1 + 512 * ks, 1), idesc_o16, ks > 0);
+      }
+    };
+    int it = 0, jg = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      mbar_wait(ld_full, (uint32_t)(it & 1));
+      for (int j = 0; j < 4; ++j, ++jg) {
+        const bool kv_pass = j < 2;
+        const int tile = j & 1;
+        mbar_wait(o_free, (uint32_t)(jg & 1) ^ 1u);  // the previous job's accumulators have been drained
+        tcgen05_fence_after();
+        for (int half = 0; half < 2; ++half) {
+          if (elect_one()) {
+            if (kv_pass) {
+              scores(RA + 128 * half, sK0, sK1, tile, sQ0, sQ1, half);   // S^T  = K_t Q^T
+              scores(RB + 128 * half, sV0, sV1, tile, sD0, sD1, half);   // dP^T = V_t dO^T
+            } else {
+              scores(RA + 128 * half, sQ0, sQ1, tile, sK0, sK1, half);   // S  = Q_t K^T
+              scores(RB + 128 * half, sD0, sD1, tile, sV0, sV1, half);   // dP = dO_t V^T
+            }
+            umma_commit<1>(&s_full[half]);
+          }
+          __syncwarp();
+        }
+        mbar_wait(p_full, (uint32_t)(jg & 1));
+        tcgen05_fence_after();
+        if (elect_one()) {
+          if (kv_pass) {
+            outputs(RA, sD0, sD1);  // dV_t = P^T dO
+            outputs(RB, sQ0, sQ1);  // dK_t = dS^T Q
+          } else {
+            outputs(RB, sK0, sK1);  // dQ_t = dS K   (accumulator in the dP region's holes)
+          }
+          umma_commit<1>(o_full);
+          if (j == 3) umma_commit<1>(ld_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================================== elementwise + output: 8 warps, thread = one row of the job
+    const int half = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // row inside the 128-row tile
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t stg = smem_u32(smem + SM::oStg) + (uint32_t)(warp * SM::kStg);
+    int it = 0, jg = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      const int b = w / H, h = w - b * H;
+      // per-query row terms of this head: lse * log2(e) and dsum
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous item's values
+      {
+        const size_t base = ((size_t)b * H + h) * T + threadIdx.x;
+        row_l2[threadIdx.x] = lse[base] * 1.4426950408889634f;
+        row_ds[threadIdx.x] = dsum[base];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int j = 0; j < 4; ++j, ++jg) {
+        const bool kv_pass = j < 2;
+        const int tile = j & 1;
+        const uint32_t ta = RA + lane_off + 128u * half, tb = RB + lane_off + 128u * half;
+        float my_l2 = 0.f, my_ds = 0.f;
+        if (!kv_pass) my_l2 = row_l2[tile * 128 + r], my_ds = row_ds[tile * 128 + r];
+        mbar_wait(&s_full[half], (uint32_t)(jg & 1));
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t vs[32], vp[32];
+          tmem_ld_32x32(ta + 32 * c, vs);
+          tmem_ld_32x32(tb + 32 * c, vp);
+          tmem_ld_wait();
+          uint32_t pk[16], dk[16];
+          const int col0 = half * 128 + 32 * c;  // first column (query in the key pass, key in the query pass)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float l0 = my_l2, l1 = my_l2, d0 = my_ds, d1 = my_ds;
+            if (kv_pass) {  // column = query: broadcast reads
+              const float2 l = *reinterpret_cast<const float2*>(row_l2 + col0 + 2 * q);
+              const float2 d = *reinterpret_cast<const float2*>(row_ds + col0 + 2 * q);
+              l0 = l.x, l1 = l.y, d0 = d.x, d1 = d.y;
+            }
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vs[2 * q]), scale_log2e, -l0));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vs[2 * q + 1]), scale_log2e, -l1));
+            const float g0 = p0 * (__uint_as_float(vp[2 * q]) - d0) * scale;
+            const float g1 = p1 * (__uint_as_float(vp[2 * q + 1]) - d1) * scale;
+            pk[q] = pack_bf16x2(p0, p1);
+            dk[q] = pack_bf16x2(g0, g1);
+          }
+          if (kv_pass) tmem_st_32x16(ta + 16 * c, pk);  // P^T (the query pass does not need P as an operand)
+          tmem_st_32x16(tb + 16 * c, dk);               // dS^T / dS
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        mbar_arrive(p_full);
+        // ---- outputs: the accumulators sit in the 64-column holes [64,128) (channels 0..63) and [192,208) (64..79)
+        mbar_wait(o_full, (uint32_t)(jg & 1));
+        tcgen05_fence_after();
+        // key pass: warps 0-3 take dV (S region), warps 4-7 dK (dP region); query pass: warps 0-3 take dQ channels
+        // 0..63, warps 4-7 channels 64..79 (dP region)
+        const uint32_t region = (kv_pass ? (half ? RB : RA) : RB) + lane_off;
+        uint32_t va[32], vb[32], o2[16];
+        const bool lo_part = kv_pass || half == 0, hi_part = has_c1 && (kv_pass || half == 1);
+        if (lo_part) {
+          tmem_ld_32x32(region + 64, va);
+          tmem_ld_32x32(region + 96, vb);
+        }
+        if (hi_part) tmem_ld_32x16(region + 192, o2);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(o_free);
+        const int slot = kv_pass ? (half ? H + h : 2 * H + h) : h;  // dK | dV | dQ column block of dqkv
+        __nv_bfloat16* obase = dqkv + ((size_t)b * T + tile * 128 + quarter * 32) * (3 * D) + (size_t)slot * hd;
+        auto flush = [&](const uint32_t* v, int ncol, int c0) {
+          const uint32_t my = stg + (uint32_t)lane * 64u;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            if (gq * 8 < ncol)
+              sts128(my + (uint32_t)((gq ^ sw) << 4),
+                     pack_bf16x2(__uint_as_float(v[8 * gq]), __uint_as_float(v[8 * gq + 1])),
+                     pack_bf16x2(__uint_as_float(v[8 * gq + 2]), __uint_as_float(v[8 * gq + 3])),
+                     pack_bf16x2(__uint_as_float(v[8 * gq + 4]), __uint_as_float(v[8 * gq + 5])),
+                     pack_bf16x2(__uint_as_float(v[8 * gq + 6]), __uint_as_float(v[8 * gq + 7])));
+          }
+          __syncwarp();
+          const int gq = lane & 3;
+          const int col = c0 + gq * 8;
+          if (gq * 8 < ncol && col < hd) {
+#pragma unroll
+            for (int pss = 0; pss < 4; ++pss) {
+              const int rr = pss * 8 + (lane >> 2);
+              const uint4 q4 = lds128_u(stg + (uint32_t)(rr * 64 + ((gq ^ ((rr >> 1) & 3)) << 4)));
+              *reinterpret_cast<uint4*>(obase + (size_t)rr * (3 * D) + col) = q4;
+            }
+          }
+          __syncwarp();
+        };
+        if (lo_part) {
+          flush(va, 32, 0);
+          flush(vb, 32, 32);
+        }
+        if (hi_part) flush(o2, 16, 64);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // 3-D bf16 tensor map over qkv viewed as {hd channels, 3H head slots, B*T tokens}
 static int make_tmap_qkv(CUtensorMap* map, const void* base, int hd, int H, uint64_t tokens, uint32_t box_ch,
                          uint32_t box_tok, CUtensorMapSwizzle swz) {
@@ -659,6 +919,57 @@ static int make_tmap_qkv(CUtensorMap* map, const void* base, int hd, int H, uint
               box_ch, box_tok);
     return DITB200_EINVAL;
   }
+  return 0;
+}
+
+bool attn_bwd_tc_supported(int T, int hd) { return T == 256 && hd % 8 == 0 && hd >= 64 && hd <= 80; }
+
+// 3-D bf16 tensor map over dout [B*T, H*hd] viewed as {hd channels, H heads, tokens}
+static int make_tmap_heads(CUtensorMap* map, const void* base, int hd, int H, uint64_t tokens, uint32_t box_ch,
+                           uint32_t box_tok, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    set_error("attention: ditb200_init() has not been called");
+    return DITB200_ENOINIT;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)hd, (cuuint64_t)H, tokens};
+  cuuint64_t strides[2] = {(cuuint64_t)hd * 2, (cuuint64_t)H * hd * 2};
+  cuuint32_t box[3] = {box_ch, 1, box_tok};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("attention_bwd: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DITB200_EINVAL;
+  }
+  return 0;
+}
+
+// dqkv from qkv, dout, lse and dsum (= rowsum(dout * out), computed by the caller) for T = 256
+int launch_attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv, int B, int T,
+                       int H, int hd, cudaStream_t st) {
+  DITB_REQUIRE(is_initialised(), DITB200_ENOINIT, "attention: ditb200_init() has not been called");
+  CUtensorMap mq0, mq1, md0, md1;
+  const uint64_t tokens = (uint64_t)B * T;
+  int rc;
+  if ((rc = make_tmap_qkv(&mq0, qkv, hd, H, tokens, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_qkv(&mq1, qkv, hd, H, tokens, 16, 256, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_tmap_heads(&md0, dout, hd, H, tokens, 64, 256, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_heads(&md1, dout, hd, H, tokens, 16, 256, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdSmem::kBytes);
+    if (e != cudaSuccess) return check_cuda(e, "attention_bwd(tcgen05) smem attribute");
+    attr_set = true;
+  }
+  int grid = num_sms();
+  if (grid > B * H) grid = B * H;
+  const float scale = (float)(1.0 / sqrt((double)hd));
+  attn_bwd_tc_kernel<<<grid, kAtThreads, AttnBwdSmem::kBytes, st>>>(mq0, mq1, md0, md1, lse, dsum,
+                                                                   reinterpret_cast<__nv_bfloat16*>(dqkv), B, H, hd, scale,
+                                                                   scale * 1.4426950408889634f);
+  DITB_LAUNCH_CHECK("attention_bwd(tcgen05)");
   return 0;
 }
 
