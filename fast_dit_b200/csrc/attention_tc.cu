@@ -802,7 +802,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_co
       {
         const size_t base = ((size_t)b * H + h) * T + threadIdx.x;
         row_l2[threadIdx.x] = lse[base] * 1.4426950408889634f;
-        row_ds[threadIdx.x] = dsum[base];
+        row_ds[threadIdx.x] = dsum[base] * scale;  // pre-scaled: dS = P * (dP * scale - dsum * scale)
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int j = 0; j < 4; ++j, ++jg) {
@@ -822,19 +822,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_co
           uint32_t pk[16], dk[16];
           const int col0 = half * 128 + 32 * c;  // first column (query in the key pass, key in the query pass)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            float l0 = my_l2, l1 = my_l2, d0 = my_ds, d1 = my_ds;
-            if (kv_pass) {  // column = query: broadcast reads
-              const float2 l = *reinterpret_cast<const float2*>(row_l2 + col0 + 2 * q);
-              const float2 d = *reinterpret_cast<const float2*>(row_ds + col0 + 2 * q);
-              l0 = l.x, l1 = l.y, d0 = d.x, d1 = d.y;
+          for (int q4 = 0; q4 < 8; ++q4) {  // four score columns at a time
+            float4 l = make_float4(my_l2, my_l2, my_l2, my_l2), d = make_float4(my_ds, my_ds, my_ds, my_ds);
+            if (kv_pass) {  // column = query: one broadcast 128-bit read each
+              l = *reinterpret_cast<const float4*>(row_l2 + col0 + 4 * q4);
+              d = *reinterpret_cast<const float4*>(row_ds + col0 + 4 * q4);
             }
-            const float p0 = ex2_approx(fmaf(__uint_as_float(vs[2 * q]), scale_log2e, -l0));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(vs[2 * q + 1]), scale_log2e, -l1));
-            const float g0 = p0 * (__uint_as_float(vp[2 * q]) - d0) * scale;
-            const float g1 = p1 * (__uint_as_float(vp[2 * q + 1]) - d1) * scale;
-            pk[q] = pack_bf16x2(p0, p1);
-            dk[q] = pack_bf16x2(g0, g1);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4]), scale_log2e, -l.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 1]), scale_log2e, -l.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 2]), scale_log2e, -l.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 3]), scale_log2e, -l.w));
+            const float g0 = p0 * fmaf(__uint_as_float(vp[4 * q4]), scale, -d.x);
+            const float g1 = p1 * fmaf(__uint_as_float(vp[4 * q4 + 1]), scale, -d.y);
+            const float g2 = p2 * fmaf(__uint_as_float(vp[4 * q4 + 2]), scale, -d.z);
+            const float g3 = p3 * fmaf(__uint_as_float(vp[4 * q4 + 3]), scale, -d.w);
+            pk[2 * q4] = pack_bf16x2(p0, p1), pk[2 * q4 + 1] = pack_bf16x2(p2, p3);
+            dk[2 * q4] = pack_bf16x2(g0, g1), dk[2 * q4 + 1] = pack_bf16x2(g2, g3);
           }
           if (kv_pass) tmem_st_32x16(ta + 16 * c, pk);  // P^T (the query pass does not need P as an operand)
           tmem_st_32x16(tb + 16 * c, dk);               // dS^T / dS

@@ -194,6 +194,32 @@ def test_attention_bwd(ops, dev, hd, H, T):
         assert rel_l2(got[:, j * D:(j + 1) * D].float(), ref[:, j * D:(j + 1) * D]) < 1.5e-2, name
 
 
+@pytest.mark.parametrize("B,H,hd", [(20, 16, 72), (37, 6, 64)])
+def test_attention_bwd_tcgen05_persistent(ops, dev, B, H, hd):
+    """The tcgen05 backward (T = 256) with more (image, head) items than SMs: every CTA runs several items, i.e.
+    both phases of every barrier and the reload of the shared Q/K/V/dO tiles; checked on a slice of the batch
+    against fp64 autograd, and run twice (no atomics: bit-identical)."""
+    T = 256
+    g = _g(17)
+    D = H * hd
+    qkv = (torch.randn(B * T, 3 * D, device=dev, generator=g) * 1.5).bfloat16()
+    dout = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+    lse = torch.empty(B, H, T, device=dev)
+    out = ops.attention(qkv, B, T, H, hd, lse=lse)
+    got = ops.attention_bwd(qkv, out, dout, lse, B, T, H, hd)
+    assert torch.isfinite(got.float()).all()
+    for b0 in (0, B - 2):  # first and last images (different CTAs / iterations)
+        sl = slice(b0 * T, (b0 + 2) * T)
+        q = qkv[sl].double().view(2, T, 3, H, hd).permute(2, 0, 3, 1, 4).contiguous().requires_grad_(True)
+        o = F.scaled_dot_product_attention(q[0], q[1], q[2]).transpose(1, 2).reshape(2 * T, D)
+        o.backward(dout[sl].double())
+        ref = q.grad.permute(1, 3, 0, 2, 4).reshape(2 * T, 3 * D)
+        for j, name in enumerate("qkv"):
+            assert rel_l2(got[sl, j * D:(j + 1) * D].float(), ref[:, j * D:(j + 1) * D]) < 1.5e-2, (name, b0)
+    again = ops.attention_bwd(qkv, out, dout, lse, B, T, H, hd)
+    assert torch.equal(got, again)
+
+
 # ---------------------------------------------------------------------------- the whole step
 def _oracle_grads(model_cpu, name, x, t, y, dout=None, loss_fn=None):
     from oracle import dit_oracle as O
