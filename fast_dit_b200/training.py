@@ -142,7 +142,10 @@ def _split_k(M, N, K, trans_w):
     ctas = 148 // cg
     kb = math.ceil(K / 64)
     best, best_cost = 1, None
-    for s in range(1, min(32, kb) + 1):
+    # measured on B200 (tools/tc_probe.py sweep, K = 8192): even when one wave holds every tile, two k-splits
+    # per tile run 10-15 % faster than one (3456 x 1152: 60.7 vs 70.8 us)
+    s_min = 2 if kb >= 64 else 1
+    for s in range(s_min, min(32, kb) + 1):
         waves = math.ceil(tiles * s / ctas)
         cost = waves / s * (1.0 + 0.03 * (s - 1))  # atomics + shorter main loops are not free
         if best_cost is None or cost < best_cost - 1e-9:
