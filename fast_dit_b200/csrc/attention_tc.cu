@@ -71,6 +71,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// two accumulator registers as a packed f32x2 operand (FFMA2 / FADD2 / FMUL2 halve the issue slots of the
+// per-element softmax arithmetic; the kernels below are issue- and MUFU-bound, not FMA-bound)
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+
 // shared-memory matrix descriptors (hi word: SBO | version 1 | layout type; lo word: address >> 4 | LBO << 16)
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // 8-row groups every 1024 B
 constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);    // 8-row groups every 256 B
@@ -247,31 +251,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as packed bf16 (in place: the
         //      16 columns chunk c of P lands on were read as part of S chunk c/2 <= c)
         const float msc = mx * scale_log2e;
-        float sum0 = 0.f, sum1 = 0.f;
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 sl2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-msc, -msc);
         uint32_t pk[16];
         for (int c = 0; c < nch; c += 2) {
           tmem_ld_wait();
           tmem_ld_32x32(trow + 32 * (c + 1), vb);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * j]), scale_log2e, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * j + 1]), scale_log2e, -msc));
-            sum0 += p0, sum1 += p1;
-            pk[j] = pack_bf16x2(p0, p1);
+            const float2 e = __ffma2_rn(f2(va[2 * j], va[2 * j + 1]), sl2, nm2);
+            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            pk[j] = pack_bf16x2(pp.x, pp.y);
           }
           tmem_st_32x16(trow + 16 * c, pk);
           tmem_ld_wait();
           if (c + 2 < nch) tmem_ld_32x32(trow + 32 * (c + 2), va);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[2 * j]), scale_log2e, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[2 * j + 1]), scale_log2e, -msc));
-            sum0 += p0, sum1 += p1;
-            pk[j] = pack_bf16x2(p0, p1);
+            const float2 e = __ffma2_rn(f2(vb[2 * j], vb[2 * j + 1]), sl2, nm2);
+            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            pk[j] = pack_bf16x2(pp.x, pp.y);
           }
           tmem_st_32x16(trow + 16 * (c + 1), pk);
         }
-        const float sum = sum0 + sum1;
+        const float sum = sum2.x + sum2.y;
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&p_full[t]);
@@ -558,7 +563,8 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
         m_run = mx;
         // ---- P = exp2((S - m) scale), row sum, P -> TMEM (bf16, in place over S)
         const float msc = mx * scale_log2e;
-        float sum0 = 0.f, sum1 = 0.f;
+        float2 sum2 = make_float2(0.f, 0.f);
+        const float2 sl2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-msc, -msc);
         uint32_t pk[16];
         tmem_ld_32x32(trow, va);
 #pragma unroll
@@ -567,24 +573,24 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
           tmem_ld_32x32(trow + 32 * (c + 1), vb);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(va[2 * q]), scale_log2e, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(va[2 * q + 1]), scale_log2e, -msc));
-            sum0 += p0, sum1 += p1;
-            pk[q] = pack_bf16x2(p0, p1);
+            const float2 e = __ffma2_rn(f2(va[2 * q], va[2 * q + 1]), sl2, nm2);
+            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            pk[q] = pack_bf16x2(pp.x, pp.y);
           }
           tmem_st_32x16(trow + 16 * c, pk);
           tmem_ld_wait();
           if (c + 2 < 4) tmem_ld_32x32(trow + 32 * (c + 2), va);
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(vb[2 * q]), scale_log2e, -msc));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(vb[2 * q + 1]), scale_log2e, -msc));
-            sum0 += p0, sum1 += p1;
-            pk[q] = pack_bf16x2(p0, p1);
+            const float2 e = __ffma2_rn(f2(vb[2 * q], vb[2 * q + 1]), sl2, nm2);
+            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+            sum2 = __fadd2_rn(sum2, pp);
+            pk[q] = pack_bf16x2(pp.x, pp.y);
           }
           tmem_st_32x16(trow + 16 * (c + 1), pk);
         }
-        l_run += sum0 + sum1;
+        l_run += sum2.x + sum2.y;
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&p_full[t]);
@@ -820,6 +826,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_co
           tmem_ld_32x32(tb + 32 * c, vp);
           tmem_ld_wait();
           uint32_t pk[16], dk[16];
+          const float2 sl2 = make_float2(scale_log2e, scale_log2e), sc2 = make_float2(scale, scale);
           const int col0 = half * 128 + 32 * c;  // first column (query in the key pass, key in the query pass)
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {  // four score columns at a time
@@ -828,14 +835,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_co
               l = *reinterpret_cast<const float4*>(row_l2 + col0 + 4 * q4);
               d = *reinterpret_cast<const float4*>(row_ds + col0 + 4 * q4);
             }
-            const float p0 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4]), scale_log2e, -l.x));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 1]), scale_log2e, -l.y));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 2]), scale_log2e, -l.z));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(vs[4 * q4 + 3]), scale_log2e, -l.w));
-            const float g0 = p0 * fmaf(__uint_as_float(vp[4 * q4]), scale, -d.x);
-            const float g1 = p1 * fmaf(__uint_as_float(vp[4 * q4 + 1]), scale, -d.y);
-            const float g2 = p2 * fmaf(__uint_as_float(vp[4 * q4 + 2]), scale, -d.z);
-            const float g3 = p3 * fmaf(__uint_as_float(vp[4 * q4 + 3]), scale, -d.w);
+            const float2 e01 = __ffma2_rn(f2(vs[4 * q4], vs[4 * q4 + 1]), sl2, make_float2(-l.x, -l.y));
+            const float2 e23 = __ffma2_rn(f2(vs[4 * q4 + 2], vs[4 * q4 + 3]), sl2, make_float2(-l.z, -l.w));
+            const float p0 = ex2_approx(e01.x), p1 = ex2_approx(e01.y), p2 = ex2_approx(e23.x), p3 = ex2_approx(e23.y);
+            const float2 t01 = __ffma2_rn(f2(vp[4 * q4], vp[4 * q4 + 1]), sc2, make_float2(-d.x, -d.y));
+            const float2 t23 = __ffma2_rn(f2(vp[4 * q4 + 2], vp[4 * q4 + 3]), sc2, make_float2(-d.z, -d.w));
+            const float2 g01 = __fmul2_rn(make_float2(p0, p1), t01), g23 = __fmul2_rn(make_float2(p2, p3), t23);
+            const float g0 = g01.x, g1 = g01.y, g2 = g23.x, g3 = g23.y;
             pk[2 * q4] = pack_bf16x2(p0, p1), pk[2 * q4 + 1] = pack_bf16x2(p2, p3);
             dk[2 * q4] = pack_bf16x2(g0, g1), dk[2 * q4 + 1] = pack_bf16x2(g2, g3);
           }
