@@ -293,7 +293,8 @@ struct TileSched {
 // rows / columns past the matrix are clipped by the tensor map.  A staging tile is reused once the bulk group
 // that read it has drained (two in flight).
 // MODE 0 bias, 1 bias+GELU, 2 bias+GELU' (second pass of GELU_DAUX over the same accumulators, into aux_out),
-// 3 (acc + bias) * aux_in with the aux_in tile fetched by TMA one round ahead.
+// 3 (acc + bias) * aux_in with the aux_in tile fetched by TMA one round ahead, 5 GELU_DAUX in ONE pass: gelu into
+// staging tile 0 -> out, gelu' into tile 1 -> aux_out (tma_ld), one tanh per element, both stores per round.
 template <int MODE, int NCH>
 __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensorMap* tma_st, const CUtensorMap* tma_ld,
                                              uint64_t* ebar, uint32_t& ephase, const uint32_t taddr0,
@@ -311,9 +312,9 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
   for (int c = 0; c < NCH; c += 2) {  // 64 columns per store
     const int col = colw + c * 32;
     if (c >= nch || col >= N) break;  // warp-uniform
-    const uint32_t tile = MODE == 3 ? stg + 4096u : stg + (uint32_t)buf * 4096u;
+    const uint32_t tile = MODE == 3 ? stg + 4096u : (MODE == 5 ? stg : stg + (uint32_t)buf * 4096u);
     if (lane == 0) {  // the store that last used this staging tile has read it
-      if (MODE == 3) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+      if (MODE == 3 || MODE == 5) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
     }
     __syncwarp();
     if (MODE == 3) mbar_wait(ebar, ephase);
@@ -341,7 +342,16 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
             }
           }
         }
-        if (MODE == 1) {
+        if (MODE == 5) {  // f <- gelu, second tile <- gelu'
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float d[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gelu_and_dgelu(f[8 * g + j], f[8 * g + j], d[j]);
+            sts128(stg + 4096u + my_off + (uint32_t)(((hh * 4 + g) ^ sw) << 4), pack_bf16x2(d[0], d[1]),
+                   pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+          }
+        } else if (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_tanh_fast(f[j]);
         } else if (MODE == 2) {
@@ -372,13 +382,14 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
     __syncwarp();
     if (lane == 0) {
       tma_store_2d(tma_st, tile, col, row0);
+      if (MODE == 5) tma_store_2d(tma_ld, stg + 4096u, col, row0);  // aux_out tile
       bulk_commit_group();
       if (MODE == 3 && c + 2 < nch && col + 64 < N) {  // next round's aux_in tile (every lane has read this one)
         mbar_arrive_expect_tx(ebar, 32 * 128);
         tma_load_2d(tma_ld, ebar, reinterpret_cast<void*>(__cvta_shared_to_generic((size_t)stg)), col + 64, row0);
       }
     }
-    if (MODE == 3) ephase ^= 1u; else buf ^= 1;
+    if (MODE == 3) ephase ^= 1u; else if (MODE != 5) buf ^= 1;
   }
 }
 
@@ -593,8 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (ep.tma_store) {  // host: bf16 outputs finished in the accumulator's row layout and stored by TMA
         if (ep.epilogue == DITB200_EPI_BIAS_GELU) EPI_TMA(1, &tma_out);
         else if (ep.epilogue == DITB200_EPI_BIAS_GELU_DAUX) {
-          EPI_TMA(1, &tma_out);   // out = gelu(acc + bias)
-          EPI_TMA(2, &tma_aux);   // aux_out = gelu'(acc + bias), second pass over the same TMEM stage
+          EPI_TMA(5, &tma_out);   // out = gelu(acc + bias), aux_out = gelu'(acc + bias): one pass, two stores per round
         } else if (ep.epilogue == DITB200_EPI_MUL_AUX) EPI_TMA(3, &tma_out);
         else EPI_TMA(0, &tma_out);
       } else if (ep.epilogue == DITB200_EPI_BIAS && !has_aux) {
