@@ -73,6 +73,7 @@ SIGNATURES = {
     "ditb200_small_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_label_embed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
+    "ditb200_ln_modulate_resid": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
     "ditb200_ln_modulate_bwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ditb200_gate_resid_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "ditb200_colsum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),

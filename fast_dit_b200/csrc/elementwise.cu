@@ -66,6 +66,72 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   }
 }
 
+// Gated residual update + LayerNorm + modulate in one pass (training forward): x_out = x + gate[b] * y is formed
+// in registers from the f32 stream and the bf16 branch output, written back once, and normalised / modulated
+// from the same registers.
+template <int NV, bool kOutBf16>
+__global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
+    const float* __restrict__ x, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+    const float* __restrict__ shift, const float* __restrict__ scale, int mod_stride, float* __restrict__ x_out,
+    void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps) {
+  constexpr int D = NV * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  const int b = row / T;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const uint2* yr = reinterpret_cast<const uint2*>(y + (size_t)row * D);
+  const float4* gr = reinterpret_cast<const float4*>(gate + (size_t)b * mod_stride);
+  float4 v[NV];
+  uint2 yv[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = ldg_stream_f4(xr + lane + 32 * j), yv[j] = yr[lane + 32 * j];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 g4 = __ldg(gr + lane + 32 * j);
+    const float2 y0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[j].x));
+    const float2 y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[j].y));
+    v[j].x = fmaf(g4.x, y0.x, v[j].x), v[j].y = fmaf(g4.y, y0.y, v[j].y);
+    v[j].z = fmaf(g4.z, y1.x, v[j].z), v[j].w = fmaf(g4.w, y1.y, v[j].w);
+    reinterpret_cast<float4*>(x_out + (size_t)row * D)[lane + 32 * j] = v[j];
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  if (out == nullptr) return;
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float a = v[j].x - mean, bb = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+  if (stats != nullptr && lane == 0) {
+    stats[2 * row] = mean;
+    stats[2 * row + 1] = rstd;
+  }
+  const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+  const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 h4 = __ldg(sh + lane + 32 * j);
+    const float4 c4 = __ldg(sc + lane + 32 * j);
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * (1.0f + c4.x) + h4.x;
+    o.y = (v[j].y - mean) * rstd * (1.0f + c4.y) + h4.y;
+    o.z = (v[j].z - mean) * rstd * (1.0f + c4.z) + h4.z;
+    o.w = (v[j].w - mean) * rstd * (1.0f + c4.w) + h4.w;
+    if constexpr (kOutBf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)row * D)[lane + 32 * j] = pk;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[lane + 32 * j] = o;
+    }
+  }
+}
+
 // Any D % 4 == 0: same mapping, row re-read from L1/L2 instead of held in registers.
 template <bool kOutBf16>
 __global__ void __launch_bounds__(256) ln_modulate_generic_kernel(
@@ -425,6 +491,42 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
   }
 #undef LN_CASE
   DITB_LAUNCH_CHECK("ln_modulate");
+  return 0;
+}
+
+extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
+                                         const float* scale, int mod_stride, float* x_out, void* out, int out_dtype,
+                                         float* stats, int B, int T, int D, float eps, void* stream) {
+  DITB_REQUIRE(x && y && gate && x_out, DITB200_EINVAL, "ln_modulate_resid: null pointer");
+  DITB_REQUIRE(out == nullptr || (shift && scale), DITB200_EINVAL, "ln_modulate_resid: out needs shift and scale");
+  DITB_REQUIRE(B > 0 && T > 0 && (D == 384 || D == 768 || D == 1024 || D == 1152), DITB200_EINVAL,
+               "ln_modulate_resid: bad shape B=%d T=%d D=%d (D in 384, 768, 1024, 1152)", B, T, D);
+  DITB_REQUIRE(mod_stride % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(gate) && aligned16(x_out) &&
+                   (!out || (aligned16(out) && aligned16(shift) && aligned16(scale))),
+               DITB200_EALIGN, "ln_modulate_resid: misaligned pointer or stride");
+  DITB_REQUIRE(out_dtype == DITB200_F32 || out_dtype == DITB200_BF16, DITB200_EINVAL, "ln_modulate_resid: bad out_dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = B * T;
+  const dim3 grid((M + 3) / 4), block(128);
+  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(y);
+  const bool bf = out_dtype == DITB200_BF16;
+#define LNR_CASE(NV)                                                                                                  \
+  case NV * 128:                                                                                                      \
+    if (bf)                                                                                                           \
+      ln_modulate_resid_kernel<NV, true><<<grid, block, 0, st>>>(x, yb, gate, shift, scale, mod_stride, x_out, out,   \
+                                                                 stats, M, T, eps);                                   \
+    else                                                                                                              \
+      ln_modulate_resid_kernel<NV, false><<<grid, block, 0, st>>>(x, yb, gate, shift, scale, mod_stride, x_out, out,  \
+                                                                  stats, M, T, eps);                                  \
+    break;
+  switch (D) {
+    LNR_CASE(3)
+    LNR_CASE(6)
+    LNR_CASE(8)
+    LNR_CASE(9)
+  }
+#undef LNR_CASE
+  DITB_LAUNCH_CHECK("ln_modulate_resid");
   return 0;
 }
 

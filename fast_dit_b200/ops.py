@@ -154,6 +154,24 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
     return out
 
 
+def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None,
+                      x_out=None, want_out: bool = True):
+    """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out)."""
+    lib = _lib_for(x)
+    M, D = x.shape
+    B = M // T
+    _chk_contig(x, y)
+    assert y.dtype == torch.bfloat16 and y.shape == x.shape
+    assert gate.stride(1) == 1 and shift.stride(1) == 1 and scale.stride(1) == 1
+    assert gate.stride(0) == shift.stride(0) == scale.stride(0)
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    out = torch.empty((M, D), device=x.device, dtype=out_dtype) if want_out else None
+    _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift), _p(scale),
+          shift.stride(0), _p(x_out), _p(out), _DT[out_dtype], _p(stats), B, T, D, float(eps), _stream())
+    return x_out, out
+
+
 # ----------------------------------------------------------------------- GEMM
 def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
          rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0,

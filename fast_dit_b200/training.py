@@ -193,29 +193,48 @@ class _DiTFunction(torch.autograd.Function):
         w = sh["w"]
         saved = []
         bf = torch.bfloat16
+        # The branch outputs y1 / y2 are kept (bf16) for backward anyway, so the proj / fc2 GEMMs write only them
+        # (plain bias epilogue through TMA) and the gated residual update x + gate * y rides in front of the NEXT
+        # LayerNorm+modulate kernel, which reads the stream regardless (ops.ln_modulate_resid).
+        fused = D in (384, 768, 1024, 1152)
+        pend = None  # (y2, g2) of the previous block, not yet added to the stream `tok`
         for i, blk in enumerate(model.blocks):
             m = mod[:, i * 6 * D:(i + 1) * 6 * D]
             sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * D:(j + 1) * D] for j in range(6))
             st1 = torch.empty((M, 2), device=dev, dtype=torch.float32)
-            hA = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=bf, stats=st1)
+            if pend is None:
+                hA = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=bf, stats=st1)
+            else:
+                tok, hA = ops.ln_modulate_resid(tok, pend[0], pend[1], sh1, sc1, T, out_dtype=bf, stats=st1)
             qkv = ops.gemm(hA, w[4 * i], blk.attn.qkv.bias)
             lse = torch.empty((N, Hh, T), device=dev, dtype=torch.float32)
             o = ops.attention(qkv, N, T, Hh, hd, lse=lse)
-            y1 = torch.empty((M, D), device=dev, dtype=bf)
-            x_mid = torch.empty_like(tok)
-            ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
-                     rows_per_gate=T, out=x_mid, aux_out=y1)
             st2 = torch.empty((M, 2), device=dev, dtype=torch.float32)
-            hB = ops.ln_modulate(x_mid, sh2, sc2, T, out_dtype=bf, stats=st2)
+            if fused:
+                y1 = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias)
+                x_mid, hB = ops.ln_modulate_resid(tok, y1, g1, sh2, sc2, T, out_dtype=bf, stats=st2)
+            else:
+                y1 = torch.empty((M, D), device=dev, dtype=bf)
+                x_mid = torch.empty_like(tok)
+                ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
+                         rows_per_gate=T, out=x_mid, aux_out=y1)
+                hB = ops.ln_modulate(x_mid, sh2, sc2, T, out_dtype=bf, stats=st2)
             a1 = torch.empty((M, w[4 * i + 2].shape[0]), device=dev, dtype=bf)
             # a1 receives gelu'(fc1 pre-activation): the backward epilogue multiplies instead of re-evaluating tanh
             u = ops.gemm(hB, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU_DAUX, aux_out=a1)
-            y2 = torch.empty((M, D), device=dev, dtype=bf)
-            x_out = torch.empty_like(tok)
-            ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x_mid, gate=g2,
-                     rows_per_gate=T, out=x_out, aux_out=y2)
-            saved.append((tok, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2))
-            tok = x_out
+            if fused:
+                y2 = ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias)
+                saved.append((tok, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2))
+                tok, pend = x_mid, (y2, g2)
+            else:
+                y2 = torch.empty((M, D), device=dev, dtype=bf)
+                x_out = torch.empty_like(tok)
+                ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x_mid, gate=g2,
+                         rows_per_gate=T, out=x_out, aux_out=y2)
+                saved.append((tok, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2))
+                tok = x_out
+        if pend is not None:  # the last block's MLP branch: only the stream update (the final layer normalises itself)
+            tok, _ = ops.ln_modulate_resid(tok, pend[0], pend[1], pend[1], pend[1], T, want_out=False)
         mf = mod[:, Ld * 6 * D:]
         fl = model.final_layer
         out = ops.final_layer(tok, mf[:, :D], mf[:, D:], fl.linear.weight, fl.linear.bias, T, p, model.out_channels)

@@ -121,6 +121,16 @@ int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, 
                         void* out, int out_dtype, float* stats, int B, int T, int D, float eps,
                         void* stream);
 
+/* Gated residual update fused in front of ditb200_ln_modulate (the training forward keeps the branch output y
+ * for backward, so the GEMM that produces it needs no residual traffic of its own):
+ *   x_out[b,t,:] = x[b,t,:] + gate[b,:] * y[b,t,:]                      (models_original.py:120-121)
+ *   out[b,t,:]   = LN(x_out[b,t,:]) * (1 + scale[b,:]) + shift[b,:]     (out == NULL: only x_out)
+ * x, x_out f32 [B*T, D] (may alias); y bf16 [B*T, D]; gate/shift/scale [B, D] slices with row stride mod_stride;
+ * out bf16 or f32; stats as in ditb200_ln_modulate.  D must be 384, 768, 1024 or 1152. */
+int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
+                              const float* scale, int mod_stride, float* x_out, void* out, int out_dtype,
+                              float* stats, int B, int T, int D, float eps, void* stream);
+
 /* Backward of ditb200_ln_modulate with respect to x, shift and scale.
  * dh[B*T, D] (dh_dtype) is the gradient of the modulated output; x, scale, stats as in the forward.
  * dx[B*T, D] f32 receives the gradient wrt x (added to dx when accumulate != 0: the residual stream's

@@ -47,6 +47,28 @@ def test_ln_modulate(ops, dev, D, out_dtype):
     assert rel_l2(stats[:, 1], (x.var(1, unbiased=False) + 1e-6).rsqrt()) < 1e-5
 
 
+@pytest.mark.parametrize("D,T", [(384, 37), (1152, 256), (768, 64), (1024, 16)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_ln_modulate_resid(ops, dev, D, T, out_dtype):
+    """x_out = x + gate * y fused in front of LayerNorm + modulate (models_original.py:120-121, 19-20)."""
+    g = torch.Generator(device=dev).manual_seed(21)
+    B = 3
+    x = torch.randn(B * T, D, device=dev, generator=g) * 2 + 0.5
+    y = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+    mod = torch.randn(B, 6 * D, device=dev, generator=g) * 0.5
+    gate, shift, scale = mod[:, 2 * D:3 * D], mod[:, :D], mod[:, D:2 * D]
+    stats = torch.empty(B * T, 2, device=dev)
+    x_out, h = ops.ln_modulate_resid(x, y, gate, shift, scale, T, out_dtype=out_dtype, stats=stats)
+    xr = x.double() + gate.double().repeat_interleave(T, 0) * y.double()
+    assert rel_l2(x_out, xr) < 1e-6
+    ln = F.layer_norm(xr, (D,), eps=1e-6)
+    ref = ln * (1 + scale.double().repeat_interleave(T, 0)) + shift.double().repeat_interleave(T, 0)
+    assert rel_l2(h.float(), ref) < (1e-5 if out_dtype == torch.float32 else 4e-3)
+    assert rel_l2(stats[:, 0], xr.mean(1)) < 1e-5
+    only, none = ops.ln_modulate_resid(x, y, gate, shift, scale, T, want_out=False)
+    assert none is None and torch.equal(only, x_out)
+
+
 @pytest.mark.parametrize("p,C,H,D", [(2, 4, 32, 1152), (4, 4, 32, 768), (8, 4, 32, 384), (2, 4, 64, 384)])
 def test_patch_embed(ops, dev, p, C, H, D):
     g = torch.Generator(device=dev).manual_seed(1)

@@ -1,7 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > gpurun_out/run.log 2>&1
-echo "=== pytest backward + kernels"
-timeout 1200 python -m pytest tests/test_backward_gpu.py tests/test_kernels_gpu.py -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | grep -v "^$" | tail -4
-echo "=== train profile c4"
-timeout 300 python tools/train_profile.py --workload c4 > gpurun_out/tp.log 2>&1; head -22 gpurun_out/tp.log
+echo "=== pytest gpu"
+timeout 1700 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | grep -v "^$" | tail -5
+echo "=== bench c4"
+timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json
+echo "=== bench c2"
+timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json
