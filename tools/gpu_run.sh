@@ -1,9 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-exec > gpurun_out/run.log 2>&1
-echo "=== pytest gpu"
-timeout 1700 python -m pytest tests -q -m gpu --timeout 300 -p no:cacheprovider 2>&1 | grep -v "^$" | tail -5
-echo "=== bench c4"
-timeout 600 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json
-echo "=== bench c2"
-timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench exit=$?"; tail -3 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json
+exec > gpurun_out/run8.log 2>&1
+nvidia-smi -L | wc -l
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 1 --warmup 3 > gpurun_out/bench_c3_n8.json 2> gpurun_out/bench_c3_n8.err; echo "exit=$?"; tail -3 gpurun_out/bench_c3_n8.err; cat gpurun_out/bench_c3_n8.json
