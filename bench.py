@@ -352,7 +352,8 @@ def run_train(args):
     rerandomise_zero_params(model)
     model = model.to(dev).train()
     opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999)
-    net = DataParallel(model) if world > 1 else model
+    gdt = torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32
+    net = DataParallel(model, grad_dtype=gdt) if world > 1 else model
     diffusion = create_diffusion("")
     g = torch.Generator().manual_seed(1000 + rank)
     x_h = torch.randn(n, 4, lat, lat, generator=g).pin_memory()
@@ -433,7 +434,7 @@ def run_train(args):
         "config": {"workload": f"{name} {lat}x{lat}x4 latent training step, {n} images/GPU (global batch {n * world}), "
                                "MSE + learned-sigma VLB loss, fused AdamW + EMA, random-init weights",
                    "step_is": "one optimizer step", "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no flush needed",
-                   "parallelism": f"dp{world}, per-block gradient all-reduce (NCCL, f32, mean) overlapped with backward"},
+                   "parallelism": f"dp{world}, per-block gradient all-reduce (NCCL, {args.grad_dtype}, mean) overlapped with backward"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "mfu_bf16": {"value": value / world * flops_img / 1e12 / tf_peak, "denominator_tflops": tf_peak,
                      "flops_per_image_G": flops_img / 1e9},
@@ -457,6 +458,8 @@ def main():
     ap.add_argument("--images", type=int, default=0, help="kept images per GPU (default: the workload's)")
     ap.add_argument("--ref-images", type=int, default=2, help="kept images per reference step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"],
+                    help="training workloads, N > 1: wire format of the gradient all-reduce (f32 = the reference's DDP)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

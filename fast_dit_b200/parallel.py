@@ -109,10 +109,16 @@ class DataParallel(torch.nn.Module):
     all-reduced (mean) asynchronously, so NCCL traffic over NVLink overlaps the rest of backward.  The
     compute stream waits for all collectives only at the end of backward."""
 
-    def __init__(self, module, process_group=None, broadcast_parameters: bool = True):
+    def __init__(self, module, process_group=None, broadcast_parameters: bool = True, grad_dtype=torch.float32):
+        """grad_dtype=torch.bfloat16 sends the buckets over NVLink as bf16 (half the bytes; the f32 arena is rounded
+        once on the way out and refilled from the averaged bf16 values).  The default, f32, is what the reference's
+        DistributedDataParallel does."""
         super().__init__()
         import torch.distributed as dist
 
+        if grad_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("grad_dtype must be torch.float32 or torch.bfloat16")
+        self.grad_dtype = grad_dtype
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -130,7 +136,9 @@ class DataParallel(torch.nn.Module):
         if key is None:  # end of backward: the compute stream must see every reduced bucket
             for work, buf, avg_done in self._pending:
                 work.wait()
-                if not avg_done:
+                if isinstance(avg_done, torch.Tensor):  # bf16 wire format: refill the f32 arena slice
+                    buf.copy_(avg_done)
+                elif not avg_done:
                     buf.div_(self.world)
             self._pending = []
             return
@@ -138,7 +146,13 @@ class DataParallel(torch.nn.Module):
         if self.world == 1:
             return
         for buf in arena.bucket(key):
-            if buf.is_cuda:  # NCCL averages in the collective
+            if buf.is_cuda and self.grad_dtype == torch.bfloat16:
+                from . import ops
+
+                wire = ops.cast_bf16(buf)
+                work = dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+                self._pending.append((work, buf, wire))
+            elif buf.is_cuda:  # NCCL averages in the collective
                 work = dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
                 self._pending.append((work, buf, True))
             else:            # gloo (CPU tests of the host logic): sum, divide afterwards
