@@ -38,7 +38,10 @@ constexpr int kEpiWarps = 8;
 constexpr int kNumThreads = 64 + 32 * kEpiWarps;
 constexpr int kEpiStageBytes = 2 * 32 * 128;             // per epilogue warp: 32 rows x 32 f32 transpose buffer, or two
                                                          // 32 x 64 bf16 TMA-store tiles
-constexpr int kSmemBudget = 232448 - 1024 - 256 - kEpiWarps * kEpiStageBytes;  // what is left for the TMA ring
+constexpr int kBarBytes = 512;                           // mbarriers, TMEM address, CLC responses
+constexpr int kClcSlots = 6;                             // cluster-launch-control responses in flight / unread
+constexpr int kClcAhead = 2;                             // queries kept in flight (their latency is about one tile)
+constexpr int kSmemBudget = 232448 - 1024 - kBarBytes - kEpiWarps * kEpiStageBytes;  // what is left for the TMA ring
 constexpr int kMnChunkBytes = 64 * kBK * 2;  // one {64 MN x 64 k} TMA box of an MN-major operand
 
 struct EpiParams {
@@ -62,7 +65,7 @@ struct TcCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kSmemBudget / kStageBytes) > 8 ? 8 : (kSmemBudget / kStageBytes);
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024 /*align slack*/ + kBarBytes;
   static_assert(BN % 64 == 0 && BN >= 64 && BN <= 256, "UMMA N / epilogue column split (32-column chunks per half)");
   // epilogue column split between the two warps of a lane quarter: [0, kHalf0) and [kHalf0, BN)
   static constexpr int kHalf0 = BN / 2;
@@ -233,6 +236,13 @@ struct TileSched {
   int F, H, r, q;           // full tiles, narrow tiles, light-CTA threshold, narrow tiles per light CTA
   int split_k, n_tiles, num_units;
   int phase, cur, end_a;
+  // dynamic mode (cluster launch control): the grid has one cluster per work unit; a running cluster finishes its
+  // own unit and then cancels clusters that have not been launched yet and does their units.  SMs that become
+  // free late (another kernel, e.g. an NCCL collective, held them) simply never receive work instead of owning a
+  // fixed share of the schedule.  Responses land in a ring of kClcSlots 16-byte slots in every CTA of the pair.
+  int dyn, role, it;        // role: 0 = producer of the leader CTA (issues the queries), 1 = producer of the peer CTA, 2 = reader
+  uint32_t clc_resp;        // shared address of the response ring
+  uint64_t *clc_full, *clc_empty;
 
   __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair) {
     P = pairs, p = pair, split_k = split;
@@ -245,9 +255,75 @@ struct TileSched {
     r = F % P;
     q = part ? max(1, bn / part) : 1;
     phase = 0, cur = p, end_a = 0;
+    dyn = 0, role = 2, it = 0;
+  }
+  template <int kCG>
+  __device__ __forceinline__ bool next_dyn(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+    int u = p;
+    if (it > 0) {  // the unit of iteration `it` is the answer to query `it`
+      const int s = (it - 1) % kClcSlots;
+      mbar_wait(&clc_full[s], (uint32_t)((it - 1) / kClcSlots) & 1u);
+      uint32_t valid, x;
+      asm volatile(
+          "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+          "ld.shared.b128 r, [%2];\n\t"
+          "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+          "selp.u32 %1, 1, 0, p1;\n\t"
+          "mov.u32 %0, 0;\n\t"
+          "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+          : "=r"(x), "=r"(valid)
+          : "r"(clc_resp + 16u * (uint32_t)s)
+          : "memory");
+      fence_proxy_async();  // the slot's next writer is the asynchronous proxy
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        if (role <= 1) mbar_arrive_expect_tx(&clc_full[s], 16);  // re-arm this CTA's slot for query it + kClcSlots
+        if constexpr (kCG == 1) mbar_arrive(&clc_empty[s]); else mbar_arrive_leader(&clc_empty[s], 0);
+      }
+      if (!valid) {
+        // queries it+1 .. it+kClcAhead-1 are still in flight (they fail too): their answers must have landed in
+        // this CTA's shared memory before the CTA may exit
+        if (role <= 1)
+          for (int j = it + 1; j < it + kClcAhead; ++j) mbar_wait(&clc_full[(j - 1) % kClcSlots], (uint32_t)((j - 1) / kClcSlots) & 1u);
+        return false;
+      }
+      u = (int)x / kCG;
+    }
+    if (role == 0) {
+      // keep kClcAhead queries in flight; query j goes into slot (j - 1) % kClcSlots once every reader is done with
+      // the slot's previous answer.  No query is issued after a failed answer has been OBSERVED (undefined by the
+      // PTX model): at this point answers up to `it` were valid.
+      for (int j = (it == 0) ? 1 : it + kClcAhead; j <= it + kClcAhead; ++j) {
+        const int s = (j - 1) % kClcSlots;
+        mbar_wait(&clc_empty[s], ((uint32_t)((j - 1) / kClcSlots) & 1u) ^ 1u);
+        if (elect_one()) {
+          if constexpr (kCG == 1)
+            asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                         ::"r"(clc_resp + 16u * (uint32_t)s), "r"(smem_u32(&clc_full[s])) : "memory");
+          else
+            asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                         ::"r"(clc_resp + 16u * (uint32_t)s), "r"(smem_u32(&clc_full[s])) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+    ++it;
+    if (split_k > 1 || part_cols == 0) {
+      const int tile = u / split_k;
+      split = u - tile * split_k;
+      m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      ncols = (part_cols && n_blk == n_tiles - 1) ? part_cols : bn;
+    } else {  // full tiles first, the narrow column last
+      split = 0;
+      if (u < F) m_blk = u / n_full, n_blk = u - m_blk * n_full, ncols = bn;
+      else m_blk = u - F, n_blk = n_full, ncols = part_cols;
+    }
+    return true;
   }
   // next unit of this CTA: tile coordinates, tile width in columns, k-split index
+  template <int kCG>
   __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+    if (dyn) return next_dyn<kCG>(bn, m_blk, n_blk, ncols, split);
     if (split_k > 1 || part_cols == 0) {  // plain round-robin
       if (cur >= num_units) return false;
       const int tile = cur / split_k;
@@ -402,7 +478,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
-               const int split_k, const int part_cols) {
+               const int split_k, const int part_cols, const int dyn) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -418,6 +494,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   uint64_t* epi_bar = bars + 2 * kStages + 5;  // [kEpiWarps] aux_in tiles landing in the epilogue staging (MUL_AUX)
+  uint64_t* clc_full = bars + 2 * kStages + 5 + kEpiWarps;  // [kClcSlots] a launch-control response has landed
+  uint64_t* clc_empty = clc_full + kClcSlots;               // [kClcSlots] (leader CTA) every reader is done with it
+  uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + kBarBytes - 16 * kClcSlots;
+  static_assert((2 * 8 + 5 + kEpiWarps + 2 * kClcSlots) * 8 + 16 * kClcSlots <= kBarBytes, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cl_rank = (kCG == 2) ? cluster_ctarank() : 0u;  // rank in the cluster: pair = rank / 2
@@ -438,7 +518,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiWarps * kCG);  // one arrive per epilogue warp of every CTA
     }
+    for (int s = 0; s < kClcSlots; ++s) {
+      mbar_init(&clc_full[s], 1);                             // this CTA's producer arms it for 16 response bytes
+      mbar_init(&clc_empty[s], kCG * (1 + kEpiWarps) + 1);  // producers and epilogue warps of the pair + the MMA warp
+    }
     fence_barrier_init();
+    if (dyn) for (int s = 0; s < kClcSlots; ++s) mbar_arrive_expect_tx(&clc_full[s], 16);
   }
   if (warp == 1) tmem_alloc<kCG>(tmem_ptr, Cfg::kTmemCols);
   tcgen05_fence_before();
@@ -451,6 +536,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int kb_per = (k_blocks + split_k - 1) / split_k;
   TileSched sched;
   sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC));
+  if (kMC == 1 && dyn) {
+    sched.dyn = 1, sched.role = (warp == 0) ? (leader ? 0 : 1) : 2;
+    sched.clc_resp = smem_u32(clc_resp), sched.clc_full = clc_full, sched.clc_empty = clc_empty;
+  }
   int m_blk, n_blk, ncols, split;
 
   // Producer and MMA roles run warp-uniform loops (every lane waits on the barriers) and elect one
@@ -462,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    while (sched.next(BN, m_blk, n_blk, ncols, split)) {
+    while (sched.next<kCG>(BN, m_blk, n_blk, ncols, split)) {
       const int row_a = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM;
       const int row_b = n_blk * BN + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
@@ -521,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
+      for (; sched.next<kCG>(BN, m_blk, n_blk, ncols, split); ++iter) {
         const uint32_t idesc = idesc0 | ((uint32_t)(ncols >> 3) << 17);
         const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
         const int acc = iter & 1;
@@ -560,7 +649,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t ephase = 0;
     uint64_t* ebar = &epi_bar[warp - 2];
     int iter = 0;
-    for (; sched.next(BN, m_blk, n_blk, ncols, split); ++iter) {
+    for (; sched.next<kCG>(BN, m_blk, n_blk, ncols, split); ++iter) {
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int row0 = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM + quarter * 32;  // first row of this warp's lane quarter
@@ -678,6 +767,16 @@ static int narrow_cols(int N, int bn, int cg, int trans_w) {
   return np;
 }
 
+// Dynamic tile scheduling through cluster launch control (see TileSched).  Off by default: with the GPU to
+// itself the static longest-first schedule is as good and has no query latency; DataParallel turns it on so that
+// the backward GEMMs share the SMs with the overlapped NCCL all-reduce.
+static int g_dynamic_sched = getenv("DITB200_GEMM_DYNAMIC") != nullptr ? 1 : 0;
+extern "C" int ditb200_set_gemm_dynamic(int on) {
+  const int prev = g_dynamic_sched;
+  g_dynamic_sched = on ? 1 : 0;
+  return prev;
+}
+
 template <int kCG, int BN, int kMC = 1>
 static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) {
   using Cfg = TcCfg<kCG, BN>;
@@ -757,10 +856,12 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
     if (clusters > max_clusters) clusters = max_clusters;
   }
   if (clusters > units) clusters = units;
+  const int dyn = (kMC == 1 && g_dynamic_sched && units > clusters) ? 1 : 0;
+  if (dyn) clusters = units;  // one cluster per unit; the running ones cancel and absorb the rest
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, taux, ep, a->M, a->N, a->K,
-                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part);
+                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part, dyn);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
 }

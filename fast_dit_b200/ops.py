@@ -209,6 +209,11 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
     return out
 
 
+def set_gemm_dynamic(on: bool) -> bool:
+    """Switch the GEMMs' tile scheduler (include/ditb200.h: ditb200_set_gemm_dynamic); returns the previous setting."""
+    return bool(L.load().ditb200_set_gemm_dynamic(1 if on else 0))
+
+
 def cast_bf16(x, out=None):
     lib = _lib_for(x)
     _chk_contig(x)

@@ -10,6 +10,7 @@ Sample k of iteration i on rank r gets the global index `i * per_iter_total + k 
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -123,6 +124,10 @@ class DataParallel(torch.nn.Module):
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self._pending = []
+        # DITB200_DDP_DYNAMIC=1: dynamic GEMM tile scheduling while collectives are in flight.  Off by default: on
+        # 2 GPUs it measured within box-to-box noise of the static schedule (data-parallel findings).
+        self.dynamic_gemm = os.environ.get("DITB200_DDP_DYNAMIC") is not None
+        self._dynamic_prev = None
         self.buckets_issued = []  # bucket keys in the order they were reduced (inspection / tests)
         if self.world > 1 and broadcast_parameters:
             with torch.no_grad():
@@ -141,10 +146,20 @@ class DataParallel(torch.nn.Module):
                 elif not avg_done:
                     buf.div_(self.world)
             self._pending = []
+            if self._dynamic_prev is not None:
+                from . import ops
+
+                ops.set_gemm_dynamic(self._dynamic_prev)
+                self._dynamic_prev = None
             return
         self.buckets_issued.append(key)
         if self.world == 1:
             return
+        if self.dynamic_gemm and self._dynamic_prev is None and arena.bucket(key)[0].is_cuda:
+            # from the first collective to the end of backward the GEMMs share the SMs with NCCL's CTAs
+            from . import ops
+
+            self._dynamic_prev = ops.set_gemm_dynamic(True)
         for buf in arena.bucket(key):
             if buf.is_cuda and self.grad_dtype == torch.bfloat16:
                 from . import ops

@@ -71,6 +71,11 @@ int ditb200_abi_version(void);
 int ditb200_init(int device);
 const char* ditb200_last_error(void);
 int ditb200_sm_count(void);
+/* GEMM tile scheduling.  0 (default): every persistent CTA pair owns a fixed, longest-first share of the tiles.
+ * 1: cluster launch control — the grid has one cluster per tile and running clusters cancel and absorb the ones
+ * not yet launched, so SMs held by another kernel (the overlapped NCCL all-reduce of a data-parallel backward,
+ * the role of torch DDP in train_options/train_original.py:149) never own tiles.  Returns the previous setting. */
+int ditb200_set_gemm_dynamic(int on);
 
 /* ---------------------------------------------------------------- embedders */
 

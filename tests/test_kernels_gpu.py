@@ -219,6 +219,28 @@ def test_gemm_tcgen05_narrow_last_column_matches_full_tiles(ops, dev):
     assert rel_l2(y256, _gemm_ref(a, w, bias, 0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,cg,bn", [(16384, 3456, 1152, 2, 256), (16384, 1152, 1152, 2, 192), (8200, 1160, 1152, 0, 0),
+                                        (16384, 1152, 1152, 1, 256), (40000, 384, 64, 2, 128)])
+def test_gemm_dynamic_tile_scheduler_matches_static(ops, dev, M, N, K, cg, bn):
+    """ditb200_set_gemm_dynamic(1): one cluster per tile, running clusters cancel and absorb the pending ones through
+    cluster launch control.  Same tiles, same k order: the result must be bit-identical to the static schedule."""
+    g = torch.Generator(device=dev).manual_seed(23)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    kw = dict(tile_n=bn, cta_group=cg) if cg else {}
+    y_static = ops.gemm(a, w, bias, out_dtype=torch.bfloat16, **kw)
+    prev = ops.set_gemm_dynamic(True)
+    try:
+        for _ in range(3):  # back-to-back launches: cancelled clusters of one grid must not leak into the next
+            y_dyn = ops.gemm(a, w, bias, out_dtype=torch.bfloat16, **kw)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_dynamic(prev)
+    assert torch.equal(y_static, y_dyn)
+    assert rel_l2(y_dyn.float()[:2048], _gemm_ref(a[:2048], w, bias, 0)) < 1e-2
+
+
 @pytest.mark.parametrize("epi", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K,T", [(1024, 1152, 1152, 256), (768, 1536, 384, 64), (200, 384, 1536, 16)])
 def test_gemm_tcgen05_epilogues(ops, dev, M, N, K, T, epi):
