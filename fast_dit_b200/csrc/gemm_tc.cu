@@ -253,7 +253,7 @@ struct TileSched {
     n_full = part ? n_tiles - 1 : n_tiles;
     F = m_tiles * n_full, H = part ? m_tiles : 0;
     r = F % P;
-    q = part ? max(1, bn / part) : 1;
+    q = part ? max(1, bn / max(part, bn / 2)) : 1;  // a narrow tile still loads the whole A tile: never cheaper than half a full one
     phase = 0, cur = p, end_a = 0;
     dyn = 0, role = 2, it = 0;
   }
@@ -886,19 +886,20 @@ static double sched_cost(int M, int N, int cg, int bn, int trans_w, int split_k)
   }
   // replay of TileSched (split_k == 1): columns assigned to every CTA
   const int F = m_tiles * (n_tiles - 1), H = m_tiles;
-  const int r = F % P, q = bn / part > 1 ? bn / part : 1;
+  const int pc = part > bn / 2 ? part : bn / 2;  // cost of a narrow tile in columns (same floor as TileSched::init)
+  const int r = F % P, q = bn / pc > 1 ? bn / pc : 1;
   int load[160];
   for (int p = 0; p < P; ++p) load[p] = (F / P + (p < r ? 1 : 0)) * bn;
   int j = 0;
   for (int p = r; p < P && j < H; ++p)
-    for (int t = 0; t < q && j < H; ++t, ++j) load[p] += part;
-  for (int p = 0; j < H; ++j, p = (p + 1 == P ? 0 : p + 1)) load[p] += part;
+    for (int t = 0; t < q && j < H; ++t, ++j) load[p] += pc;
+  for (int p = 0; j < H; ++j, p = (p + 1 == P ? 0 : p + 1)) load[p] += pc;
   int mx = 0;
   for (int p = 0; p < P; ++p) mx = load[p] > mx ? load[p] : mx;
   return (double)mx / eff;
 }
 
-static void choose_tile(int M, int N, int trans_w, int split_k, int* cg_out, int* bn_out) {
+static void choose_tile(int M, int N, int K, int trans_w, int split_k, int* cg_out, int* bn_out) {
   const int cg = (M > kBM) ? 2 : 1;
   *cg_out = cg;
   const int cand[3] = {256, 192, 128};
@@ -909,8 +910,9 @@ static void choose_tile(int M, int N, int trans_w, int split_k, int* cg_out, int
     if (trans_w && (bn / cg) % 64 != 0) continue;   // MN-major B: 64-column boxes per CTA
     if (bn > 128 && N <= bn - 64) continue;          // a tile wider than the matrix buys nothing
     double c = sched_cost(M, N, cg, bn, trans_w, split_k);
-    // measured: with few tile columns an exact 192-wide cover beats 256 + a narrow column by 3-8 % (N = 1152)
-    if (bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048) c *= 0.8;
+    // measured (N = 1152, M = 16384): with a long k loop an exact 192-wide cover beats 256 + a narrow column
+    // (K = 4608: 134.1 vs 136.4 us); with a short one the shorter schedule of 256 + narrow wins (K = 1152: 39.5 vs 41.4)
+    if (bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048 && K > 2048) c *= 0.8;
     if (c < best) best = c, best_bn = bn;
   }
   *bn_out = best_bn;
@@ -951,7 +953,7 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   int cg = a->cta_group, bn = a->tile_n;
   if (cg == 0 || bn == 0) {
     int acg, abn;
-    choose_tile(a->M, a->N, a->trans_w, split_k, &acg, &abn);
+    choose_tile(a->M, a->N, a->K, a->trans_w, split_k, &acg, &abn);
     if (cg == 0) cg = acg;
     if (bn == 0) bn = abn;
   }
