@@ -252,6 +252,72 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(
   }
 }
 
+// K = C*p*p = 16 (every /2 model): a thread keeps the weight rows of 4 consecutive hidden channels in registers
+// (64 values) and runs over the group's tokens: 4 broadcast 128-bit shared loads feed 64 FMAs (the kernel above
+// spends one such load per 4 FMAs and is bound by the shared-memory pipe), and bias / pos / out move as float4.
+// Same k order and the same fmaf chain per output as the general kernel: bit-identical results.
+__global__ void __launch_bounds__(320) patch_embed_k16_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    const float* __restrict__ pos, float* __restrict__ out, int B, int C, int H, int W, int p,
+    int D, int round_bf16) {
+  __shared__ __align__(16) float patch[kPeTok * 16];
+  const int Hp = H / p, Wp = W / p, T = Hp * Wp;
+  const int M = B * T;
+  const int tok0 = blockIdx.x * kPeTok;
+  for (int idx = threadIdx.x; idx < kPeTok * 16; idx += blockDim.x) {
+    const int tt = idx >> 4, k = idx & 15;
+    const int tok = tok0 + tt;
+    float v = 0.f;
+    if (tok < M) {
+      const int b = tok / T, t = tok - b * T;
+      const int hp = t / Wp, wp = t - hp * Wp;
+      const int c = k / (p * p), r = k - c * p * p;
+      const int i = r / p, j = r - i * p;
+      v = x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j];
+      if (round_bf16) v = bf16_round(v);
+    }
+    patch[idx] = v;
+  }
+  __syncthreads();
+  const int d0 = threadIdx.x * 4;
+  if (d0 >= D) return;
+  float wq[4][16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+      float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + q) * 16 + k));
+      if (round_bf16) w4 = make_float4(bf16_round(w4.x), bf16_round(w4.y), bf16_round(w4.z), bf16_round(w4.w));
+      wq[q][k] = w4.x, wq[q][k + 1] = w4.y, wq[q][k + 2] = w4.z, wq[q][k + 3] = w4.w;
+    }
+  }
+  float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + d0));
+  if (round_bf16) b4 = make_float4(bf16_round(b4.x), bf16_round(b4.y), bf16_round(b4.z), bf16_round(b4.w));
+  const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll 2
+  for (int tt = 0; tt < kPeTok; ++tt) {
+    const int tok = tok0 + tt;
+    if (tok >= M) break;
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&patch[tt * 16 + k]);
+      pv[k] = p4.x, pv[k + 1] = p4.y, pv[k + 2] = p4.z, pv[k + 3] = p4.w;
+    }
+    const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(tok % T) * D + d0));
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(wq[q][k], pv[k], acc);
+      acc += bq[q];
+      r[q] = round_bf16 ? bf16_round(acc) : acc;
+    }
+    *reinterpret_cast<float4*>(out + (size_t)tok * D + d0) = make_float4(r[0] + ps.x, r[1] + ps.y, r[2] + ps.z, r[3] + ps.w);
+  }
+}
+
 // ============================================================= timestep sinusoid
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out,
                                           int B, int dim, float neg_log_period) {
@@ -545,6 +611,13 @@ extern "C" int ditb200_patch_embed(const float* x, const float* w, const float* 
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "patch_embed smem attr");
   }
+  if (K == 16 && D % 4 == 0 && D / 4 <= 320 && aligned16(w) && aligned16(bias) && aligned16(pos) && aligned16(out)) {
+    const int threads = (D / 4 + 31) / 32 * 32;
+    patch_embed_k16_kernel<<<(M + kPeTok - 1) / kPeTok, threads, 0, (cudaStream_t)stream>>>(
+        x, w, bias, pos, out, B, C, H, W, p, D, round_bf16);
+    DITB_LAUNCH_CHECK("patch_embed");
+    return 0;
+  }
   patch_embed_kernel<<<(M + kPeTok - 1) / kPeTok, 256, smem, (cudaStream_t)stream>>>(
       x, w, bias, pos, out, B, C, H, W, p, D, round_bf16);
   DITB_LAUNCH_CHECK("patch_embed");
@@ -625,58 +698,59 @@ __global__ void __launch_bounds__(256) final_layer_rows_kernel(
     reinterpret_cast<float4*>(ws)[i] = v;
   }
   __syncthreads();
-  const int W = gridDim.x * 8;
-  int row = blockIdx.x * 8 + warp;
-  if (row >= M) return;
+  const int W = gridDim.x * 8;  // warps in the grid
   const int Wp = (int)(sqrtf((float)T) + 0.5f), Himg = Wp * p;
   const float b_o = bias[lane];
-  float4 v[NV], nx[NV];
-  {
-    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  // Two rows per warp and pass: every 128-bit weight read from shared memory feeds 8 FMAs instead of 4 (the weight
+  // re-read per row, 32 x D x 4 bytes, is what bounds this kernel: shared-memory pipe, not HBM).
+  for (int row0 = 2 * (blockIdx.x * 8 + warp); row0 < M; row0 += 2 * W) {
+    const bool two = row0 + 1 < M;
+    float4 v[2][NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = ldg_stream_f4(xr + lane + 32 * j);
-  }
-  for (; row < M; row += W) {
-    if (row + W < M) {
-      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(row + W) * D);
+    for (int r = 0; r < 2; ++r) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)(row0 + (two ? r : 0)) * D);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) nx[j] = ldg_stream_f4(xr + lane + 32 * j);
+      for (int j = 0; j < NV; ++j) v[r][j] = ldg_stream_f4(xr + lane + 32 * j);
     }
-    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
+      for (int j = 0; j < NV; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+      const float mean = warp_sum(s) * (1.0f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+      const int b = (row0 + (two ? r : 0)) / T;
+      const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
+      const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 h4 = __ldg(sh + lane + 32 * j), c4 = __ldg(sc + lane + 32 * j);
+        float4& u = v[r][j];
+        u.x = (u.x - mean) * rstd * (1.0f + c4.x) + h4.x;
+        u.y = (u.y - mean) * rstd * (1.0f + c4.y) + h4.y;
+        u.z = (u.z - mean) * rstd * (1.0f + c4.z) + h4.z;
+        u.w = (u.w - mean) * rstd * (1.0f + c4.w) + h4.w;
+        if (round_bf16) u.x = bf16_round(u.x), u.y = bf16_round(u.y), u.z = bf16_round(u.z), u.w = bf16_round(u.w);
+      }
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
-    const int b = row / T, t = row - b * T;
-    const float4* sh = reinterpret_cast<const float4*>(shift + (size_t)b * mod_stride);
-    const float4* sc = reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride);
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const float4 h4 = __ldg(sh + lane + 32 * j), c4 = __ldg(sc + lane + 32 * j);
-      v[j].x = (v[j].x - mean) * rstd * (1.0f + c4.x) + h4.x;
-      v[j].y = (v[j].y - mean) * rstd * (1.0f + c4.y) + h4.y;
-      v[j].z = (v[j].z - mean) * rstd * (1.0f + c4.z) + h4.z;
-      v[j].w = (v[j].w - mean) * rstd * (1.0f + c4.w) + h4.w;
-      if (round_bf16)
-        v[j].x = bf16_round(v[j].x), v[j].y = bf16_round(v[j].y), v[j].z = bf16_round(v[j].z), v[j].w = bf16_round(v[j].w);
-    }
-    float acc[32];
+    float acc0[32], acc1[32];
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
       const float4* wr = reinterpret_cast<const float4*>(ws + (size_t)o * D);
-      float a = 0.f;
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const float4 w4 = wr[lane + 32 * j];
-        a = fmaf(v[j].x, w4.x, a), a = fmaf(v[j].y, w4.y, a), a = fmaf(v[j].z, w4.z, a), a = fmaf(v[j].w, w4.w, a);
+        a0 = fmaf(v[0][j].x, w4.x, a0), a0 = fmaf(v[0][j].y, w4.y, a0), a0 = fmaf(v[0][j].z, w4.z, a0), a0 = fmaf(v[0][j].w, w4.w, a0);
+        a1 = fmaf(v[1][j].x, w4.x, a1), a1 = fmaf(v[1][j].y, w4.y, a1), a1 = fmaf(v[1][j].z, w4.z, a1), a1 = fmaf(v[1][j].w, w4.w, a1);
       }
-      acc[o] = a;
+      acc0[o] = a0, acc1[o] = a1;
     }
     // transpose-reduce: after the step with distance s, entry i of a lane holds the sum over its 32/s-lane group of
     // output (i + the bits of `lane` already consumed); 16 + 8 + 4 + 2 + 1 shuffles leave output `lane` in acc[0]
@@ -685,17 +759,22 @@ __global__ void __launch_bounds__(256) final_layer_rows_kernel(
       const bool up = (lane & s2) != 0;
 #pragma unroll
       for (int i = 0; i < s2; ++i) {
-        const float keep = up ? acc[i + s2] : acc[i];
-        const float send = up ? acc[i] : acc[i + s2];
-        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+        const float keep0 = up ? acc0[i + s2] : acc0[i], send0 = up ? acc0[i] : acc0[i + s2];
+        const float keep1 = up ? acc1[i + s2] : acc1[i], send1 = up ? acc1[i] : acc1[i + s2];
+        acc0[i] = keep0 + __shfl_xor_sync(0xffffffffu, send0, s2);
+        acc1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, s2);
       }
     }
     // output o = lane: (pi, pj, c) = unpatchify order (models_original.py:228-230)
     const int c = lane % Cout, pq = lane / Cout, pi = pq / p, pj = pq - pi * p;
-    const int hh = t / Wp, ww = t - hh * Wp;
-    out[(((size_t)b * Cout + c) * Himg + hh * p + pi) * Himg + ww * p + pj] = acc[0] + b_o;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) v[j] = nx[j];
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !two) break;
+      const int row = row0 + r;
+      const int b = row / T, t = row - b * T;
+      const int hh = t / Wp, ww = t - hh * Wp;
+      out[(((size_t)b * Cout + c) * Himg + hh * p + pi) * Himg + ww * p + pj] = (r ? acc1[0] : acc0[0]) + b_o;
+    }
   }
 }
 
@@ -719,7 +798,7 @@ extern "C" int ditb200_final_layer(const float* x, const float* shift, const flo
   if (NO == 32 && D % 128 == 0 && aligned16(w) && (D / 128 == 3 || D / 128 == 6 || D / 128 == 8 || D / 128 == 9)) {
     const size_t smem = (size_t)32 * D * sizeof(float);
     int g = num_sms() > 0 ? num_sms() : 148;
-    if (g > (M + 7) / 8) g = (M + 7) / 8;
+    if (g > (M + 15) / 16) g = (M + 15) / 16;  // 8 warps x 2 rows per CTA and pass
 #define FLR_CASE(NV)                                                                                           \
   case NV: {                                                                                                   \
     cudaError_t e = cudaFuncSetAttribute(final_layer_rows_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

@@ -137,23 +137,40 @@ __global__ void __launch_bounds__(256) gemm_simt_small_m_kernel(const SimtArgs p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   float acc0 = 0.f, acc1 = 0.f;
-  for (int k0 = 0; k0 < p.K; k0 += kSmK) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 64 * kSmK; idx += 256) {
+  // The next k slab travels global -> registers while the current one is multiplied out of shared memory: the
+  // kernel is a chain of K / 128 short slabs, and without the overlap each one pays a full memory latency.
+  float ra[64 * kSmK / 256], rw[8 * kSmK / 256];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 64 * kSmK / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i;
       const int r = idx / kSmK, k = idx - r * kSmK;
-      float v = 0.f;
-      if (r < p.M && k0 + k < p.K) {
-        v = p.a[(size_t)r * p.lda + k0 + k];
-        if (p.silu_in) v = silu_acc(v);
-      }
-      As[r][k] = v;
+      ra[i] = (r < p.M && k0 + k < p.K) ? p.a[(size_t)r * p.lda + k0 + k] : 0.f;
     }
-    for (int idx = threadIdx.x; idx < 8 * kSmK; idx += 256) {
+#pragma unroll
+    for (int i = 0; i < 8 * kSmK / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i;
       const int c = idx / kSmK, k = idx - c * kSmK;
       const int nn = blockIdx.x * 8 + c;
-      Ws[c][k] = (nn < p.N && k0 + k < p.K) ? load_w(p.w, p.w_bf16, (size_t)nn * p.K + k0 + k) : 0.f;
+      rw[i] = (nn < p.N && k0 + k < p.K) ? load_w(p.w, p.w_bf16, (size_t)nn * p.K + k0 + k) : 0.f;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < p.K; k0 += kSmK) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 64 * kSmK / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i;
+      const int r = idx / kSmK, k = idx - r * kSmK;
+      As[r][k] = (p.silu_in && r < p.M && k0 + k < p.K) ? silu_acc(ra[i]) : ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8 * kSmK / 256; ++i) {
+      const int idx = threadIdx.x + 256 * i;
+      Ws[idx / kSmK][idx % kSmK] = rw[i];
     }
     __syncthreads();
+    if (k0 + kSmK < p.K) fetch(k0 + kSmK);
 #pragma unroll
     for (int kc = 0; kc < kSmK; kc += 32) {
       float p0 = 0.f, p1 = 0.f;
