@@ -255,66 +255,86 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(
 // K = C*p*p = 16 (every /2 model): a thread keeps the weight rows of 4 consecutive hidden channels in registers
 // (64 values) and runs over the group's tokens: 4 broadcast 128-bit shared loads feed 64 FMAs (the kernel above
 // spends one such load per 4 FMAs and is bound by the shared-memory pipe), and bias / pos / out move as float4.
+// Persistent CTAs: the weights are fetched once, and the 16 pos rows of a token group are requested before the
+// patch gather so that a group pays one memory latency, not one per token (ncu: 72 us -> latency-bound on pos).
 // Same k order and the same fmaf chain per output as the general kernel: bit-identical results.
-__global__ void __launch_bounds__(320) patch_embed_k16_kernel(
+__global__ void __launch_bounds__(320, 1) patch_embed_k16_kernel(
     const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
     const float* __restrict__ pos, float* __restrict__ out, int B, int C, int H, int W, int p,
     int D, int round_bf16) {
   __shared__ __align__(16) float patch[kPeTok * 16];
   const int Hp = H / p, Wp = W / p, T = Hp * Wp;
   const int M = B * T;
-  const int tok0 = blockIdx.x * kPeTok;
-  for (int idx = threadIdx.x; idx < kPeTok * 16; idx += blockDim.x) {
-    const int tt = idx >> 4, k = idx & 15;
-    const int tok = tok0 + tt;
-    float v = 0.f;
-    if (tok < M) {
-      const int b = tok / T, t = tok - b * T;
-      const int hp = t / Wp, wp = t - hp * Wp;
-      const int c = k / (p * p), r = k - c * p * p;
-      const int i = r / p, j = r - i * p;
-      v = x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j];
-      if (round_bf16) v = bf16_round(v);
-    }
-    patch[idx] = v;
-  }
-  __syncthreads();
   const int d0 = threadIdx.x * 4;
-  if (d0 >= D) return;
+  const bool active = d0 < D;
   float wq[4][16];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int k = 0; k < 16; k += 4) {
-      float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + q) * 16 + k));
-      if (round_bf16) w4 = make_float4(bf16_round(w4.x), bf16_round(w4.y), bf16_round(w4.z), bf16_round(w4.w));
-      wq[q][k] = w4.x, wq[q][k + 1] = w4.y, wq[q][k + 2] = w4.z, wq[q][k + 3] = w4.w;
-    }
-  }
-  float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + d0));
-  if (round_bf16) b4 = make_float4(bf16_round(b4.x), bf16_round(b4.y), bf16_round(b4.z), bf16_round(b4.w));
-  const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll 2
-  for (int tt = 0; tt < kPeTok; ++tt) {
-    const int tok = tok0 + tt;
-    if (tok >= M) break;
-    float pv[16];
-#pragma unroll
-    for (int k = 0; k < 16; k += 4) {
-      const float4 p4 = *reinterpret_cast<const float4*>(&patch[tt * 16 + k]);
-      pv[k] = p4.x, pv[k + 1] = p4.y, pv[k + 2] = p4.z, pv[k + 3] = p4.w;
-    }
-    const float4 ps = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(tok % T) * D + d0));
-    float r[4];
+  float bq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) acc = fmaf(wq[q][k], pv[k], acc);
-      acc += bq[q];
-      r[q] = round_bf16 ? bf16_round(acc) : acc;
+      for (int k = 0; k < 16; k += 4) {
+        float4 w4 = __ldg(reinterpret_cast<const float4*>(w + (size_t)(d0 + q) * 16 + k));
+        if (round_bf16) w4 = make_float4(bf16_round(w4.x), bf16_round(w4.y), bf16_round(w4.z), bf16_round(w4.w));
+        wq[q][k] = w4.x, wq[q][k + 1] = w4.y, wq[q][k + 2] = w4.z, wq[q][k + 3] = w4.w;
+      }
     }
-    *reinterpret_cast<float4*>(out + (size_t)tok * D + d0) = make_float4(r[0] + ps.x, r[1] + ps.y, r[2] + ps.z, r[3] + ps.w);
+    float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + d0));
+    if (round_bf16) b4 = make_float4(bf16_round(b4.x), bf16_round(b4.y), bf16_round(b4.z), bf16_round(b4.w));
+    bq[0] = b4.x, bq[1] = b4.y, bq[2] = b4.z, bq[3] = b4.w;
+  }
+  const int groups = (M + kPeTok - 1) / kPeTok;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int tok0 = g * kPeTok;
+    float4 ps[kPeTok];
+    if (active) {
+#pragma unroll
+      for (int tt = 0; tt < kPeTok; ++tt) {
+        const int tok = min(tok0 + tt, M - 1);
+        ps[tt] = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(tok % T) * D + d0));
+      }
+    }
+    for (int idx = threadIdx.x; idx < kPeTok * 16; idx += blockDim.x) {
+      const int tt = idx >> 4, k = idx & 15;
+      const int tok = tok0 + tt;
+      float v = 0.f;
+      if (tok < M) {
+        const int b = tok / T, t = tok - b * T;
+        const int hp = t / Wp, wp = t - hp * Wp;
+        const int c = k / (p * p), r = k - c * p * p;
+        const int i = r / p, j = r - i * p;
+        v = x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j];
+        if (round_bf16) v = bf16_round(v);
+      }
+      patch[idx] = v;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int tt = 0; tt < kPeTok; ++tt) {
+        const int tok = tok0 + tt;
+        if (tok < M) {
+          float pv[16];
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(&patch[tt * 16 + k]);
+            pv[k] = p4.x, pv[k + 1] = p4.y, pv[k + 2] = p4.z, pv[k + 3] = p4.w;
+          }
+          float r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc = fmaf(wq[q][k], pv[k], acc);
+            acc += bq[q];
+            r[q] = round_bf16 ? bf16_round(acc) : acc;
+          }
+          *reinterpret_cast<float4*>(out + (size_t)tok * D + d0) =
+              make_float4(r[0] + ps[tt].x, r[1] + ps[tt].y, r[2] + ps[tt].z, r[3] + ps[tt].w);
+        }
+      }
+    }
+    __syncthreads();  // the next group's gather overwrites `patch`
   }
 }
 
@@ -613,7 +633,9 @@ extern "C" int ditb200_patch_embed(const float* x, const float* w, const float* 
   }
   if (K == 16 && D % 4 == 0 && D / 4 <= 320 && aligned16(w) && aligned16(bias) && aligned16(pos) && aligned16(out)) {
     const int threads = (D / 4 + 31) / 32 * 32;
-    patch_embed_k16_kernel<<<(M + kPeTok - 1) / kPeTok, threads, 0, (cudaStream_t)stream>>>(
+    int g = num_sms() > 0 ? num_sms() : 148;
+    if (g > (M + kPeTok - 1) / kPeTok) g = (M + kPeTok - 1) / kPeTok;
+    patch_embed_k16_kernel<<<g, threads, 0, (cudaStream_t)stream>>>(
         x, w, bias, pos, out, B, C, H, W, p, D, round_bf16);
     DITB_LAUNCH_CHECK("patch_embed");
     return 0;
@@ -705,6 +727,11 @@ __global__ void __launch_bounds__(256) final_layer_rows_kernel(
   // re-read per row, 32 x D x 4 bytes, is what bounds this kernel: shared-memory pipe, not HBM).
   for (int row0 = 2 * (blockIdx.x * 8 + warp); row0 < M; row0 += 2 * W) {
     const bool two = row0 + 1 < M;
+    if (row0 + 2 * W < M) {  // pull the next pair of rows towards L2 (no registers left for a software prefetch)
+      const char* nxt = reinterpret_cast<const char*>(x + (size_t)(row0 + 2 * W) * D);
+      const int bytes = (row0 + 2 * W + 1 < M ? 2 : 1) * D * 4;
+      for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+    }
     float4 v[2][NV];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {

@@ -1,11 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > gpurun_out/run2.log 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py > gpurun_out/bench_c3_v8.json 2>gpurun_out/bench_err.log
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_c3_v8.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['clocks'])
-print(d['kernel_breakdown_ms_per_denoise_step'])
-PY
+L=fast_dit_b200/lib/libditb200.so
+for v in cur k192 cur k192; do
+  cp ab/libditb200_$v.so $L
+  echo "== $v"
+  timeout 300 python bench.py --workload c4 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('   ', round(d['value'],1),'img/s', round(d['ms_per_step'],2),'ms/step')"
+done
+cp ab/libditb200_cur.so $L
