@@ -1,14 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > gpurun_out/run2.log 2>&1
-L=fast_dit_b200/lib/libditb200.so
-for v in cur k192 cur k192; do
-  cp ab/libditb200_$v.so $L
-  echo "== $v"
-  timeout 300 python bench.py --workload c4 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('   ', round(d['value'],1),'img/s', round(d['ms_per_step'],2),'ms/step')"
+DITB200_ATTN_DIRECT_OUT=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -x -k "attention" 2>&1 | tail -2
+for rep in 1 2; do
+echo "== staged"; timeout 120 python tools/attn_probe.py --iters 100 2>&1 | tail -1
+echo "== direct"; DITB200_ATTN_DIRECT_OUT=1 timeout 120 python tools/attn_probe.py --iters 100 2>&1 | tail -1
 done
-cp ab/libditb200_cur.so $L
+echo "== staged T128"; timeout 120 python tools/attn_probe.py --iters 100 --t 128 --b 256 2>&1 | tail -1
+echo "== direct T128"; DITB200_ATTN_DIRECT_OUT=1 timeout 120 python tools/attn_probe.py --iters 100 --t 128 --b 256 2>&1 | tail -1
