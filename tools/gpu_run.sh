@@ -1,10 +1,11 @@
 #!/bin/bash
+# Standard verification pass on a GPU box (run through gpurun from the repo root):
+#   gpurun --timeout 1800 -- 'bash tools/gpu_run.sh'
+# GPU parity tests, the smoke entry point, then the default bench line; everything lands in gpurun_out/.
+# Every step runs under its own timeout so that a hung kernel cannot hold the box.
 mkdir -p gpurun_out
-exec > gpurun_out/run2.log 2>&1
-DITB200_ATTN_DIRECT_OUT=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q -x -k "attention" 2>&1 | tail -2
-for rep in 1 2; do
-echo "== staged"; timeout 120 python tools/attn_probe.py --iters 100 2>&1 | tail -1
-echo "== direct"; DITB200_ATTN_DIRECT_OUT=1 timeout 120 python tools/attn_probe.py --iters 100 2>&1 | tail -1
-done
-echo "== staged T128"; timeout 120 python tools/attn_probe.py --iters 100 --t 128 --b 256 2>&1 | tail -1
-echo "== direct T128"; DITB200_ATTN_DIRECT_OUT=1 timeout 120 python tools/attn_probe.py --iters 100 --t 128 --b 256 2>&1 | tail -1
+exec > gpurun_out/verify.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 600 python bench.py > gpurun_out/bench_c3.json 2> gpurun_out/bench_err.log
+tail -c 600 gpurun_out/bench_c3.json
