@@ -249,7 +249,7 @@ struct TileSched {
   uint32_t clc_resp;        // shared address of the response ring
   uint64_t *clc_full, *clc_empty;
 
-  __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair) {
+  __host__ __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair) {
     P = pairs, p = pair, split_k = split;
     const int m_tiles = (M + tile_m - 1) / tile_m;
     n_tiles = (N + bn - 1) / bn;
@@ -328,8 +328,10 @@ struct TileSched {
   }
   // next unit of this CTA: tile coordinates, tile width in columns, k-split index
   template <int kCG>
-  __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+  __host__ __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+#ifdef __CUDA_ARCH__
     if (dyn) return next_dyn<kCG>(bn, m_blk, n_blk, ncols, split);
+#endif
     if (tail_parts > 1) {  // split_k == 1, no narrow column: whole tiles round-robin, then the tail tiles in parts
       const int u = cur;
       if (u >= tail_first + (num_units - tail_first) * tail_parts) return false;
@@ -874,6 +876,26 @@ extern "C" int ditb200_set_gemm_dynamic(int on) {
   const int prev = g_dynamic_sched;
   g_dynamic_sched = on ? 1 : 0;
   return prev;
+}
+
+// Host replay of the static tile schedules (the very TileSched the kernel runs): for every CTA pair p the units it
+// would process, in order, as rows {p, m_blk, n_blk, ncols, k_part}.  Test hook: coverage and balance of the
+// schedule can be checked without a GPU (tests/test_host_logic.py).  Returns the number of rows (or -needed).
+extern "C" int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols, int split_k, int pairs,
+                                           int tail_units, int tail_parts, int* rows, int cap) {
+  if (M <= 0 || N <= 0 || tile_m <= 0 || bn <= 0 || split_k <= 0 || pairs <= 0 || part_cols < 0 || part_cols >= bn) return 0;
+  int n = 0;
+  for (int p = 0; p < pairs; ++p) {
+    TileSched sc;
+    sc.init(M, N, tile_m, bn, part_cols, split_k, pairs, p);
+    if (tail_parts > 1) sc.tail_first = sc.num_units - tail_units, sc.tail_parts = tail_parts;
+    int m_blk = 0, n_blk = 0, ncols = 0, split = 0;
+    while (sc.next<1>(bn, m_blk, n_blk, ncols, split)) {
+      if (rows && n < cap) rows[5 * n] = p, rows[5 * n + 1] = m_blk, rows[5 * n + 2] = n_blk, rows[5 * n + 3] = ncols, rows[5 * n + 4] = split;
+      ++n;
+    }
+  }
+  return (rows && n > cap) ? -n : n;
 }
 
 template <int kCG, int BN, int kMC = 1>

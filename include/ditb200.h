@@ -76,6 +76,12 @@ int ditb200_sm_count(void);
  * not yet launched, so SMs held by another kernel (the overlapped NCCL all-reduce of a data-parallel backward,
  * the role of torch DDP in train_options/train_original.py:149) never own tiles.  Returns the previous setting. */
 int ditb200_set_gemm_dynamic(int on);
+/* Test hook (host only, no GPU needed): replays the GEMM kernel's static tile schedule for `pairs` CTA pairs and
+ * writes, for every pair in order, the units it would process as rows {pair, m_blk, n_blk, ncols, k_part} into
+ * rows[5 * cap].  part_cols = width of the narrow last tile column (0: none); tail_units / tail_parts describe the
+ * opt-in tail-only split-K (1 part = off).  Returns the number of rows, or -needed when cap is too small. */
+int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols, int split_k, int pairs,
+                                int tail_units, int tail_parts, int* rows, int cap);
 
 /* ---------------------------------------------------------------- embedders */
 

@@ -102,3 +102,69 @@ def test_model_refuses_cpu_inputs():
     m = DiT_models["DiT-S/8"](input_size=16, num_classes=10).eval()
     with pytest.raises(Ditb200Error):
         m(torch.randn(2, 4, 16, 16), torch.zeros(2, dtype=torch.long), torch.zeros(2, dtype=torch.long))
+
+
+# ------------------------------------------------------------------ GEMM tile schedule (host replay of the kernel's TileSched)
+def _schedule(M, N, tile_m, bn, part, split_k, pairs, tail_units=0, tail_parts=1):
+    import ctypes
+    from fast_dit_b200 import _lib as L
+
+    lib = L.load()
+    cap = 1 << 16
+    buf = (ctypes.c_int * (5 * cap))()
+    n = lib.ditb200_debug_tile_schedule(M, N, tile_m, bn, part, split_k, pairs, tail_units, tail_parts,
+                                        ctypes.cast(buf, ctypes.c_void_p), cap)
+    assert 0 < n <= cap
+    return np.frombuffer(buf, dtype=np.int32)[: 5 * n].reshape(n, 5).copy()
+
+
+@pytest.mark.parametrize("M,N,bn,part,split_k", [
+    (16384, 3456, 256, 128, 1),   # qkv at C3: 13 full columns + a 128-wide one
+    (16384, 1152, 256, 128, 1),   # proj
+    (16384, 1152, 192, 0, 1),     # fc2: exact 192-wide cover
+    (16384, 4608, 256, 0, 1),     # fc1
+    (8200, 1160, 192, 16, 1),     # ragged rows, 16-wide last column
+    (1152, 4608, 256, 0, 4),      # weight gradient, split-K
+    (300, 384, 256, 128, 1),      # fewer tiles than CTA pairs
+])
+def test_gemm_static_schedule_covers_every_tile_once(M, N, bn, part, split_k):
+    """Every (tile row, tile column, k part) is processed by exactly one CTA pair, the narrow last column has the
+    width the host computed, and the longest-first order leaves no pair more than one full tile behind."""
+    tile_m, pairs = 256, 74
+    rows = _schedule(M, N, tile_m, bn, part, split_k, pairs)
+    m_tiles, n_tiles = -(-M // tile_m), -(-N // bn)
+    keys = [tuple(r[[1, 2, 4]]) for r in rows]
+    assert len(keys) == len(set(keys)) == m_tiles * n_tiles * split_k
+    assert {k[0] for k in keys} == set(range(m_tiles)) and {k[1] for k in keys} == set(range(n_tiles))
+    last = rows[rows[:, 2] == n_tiles - 1]
+    assert (last[:, 3] == (part if part else bn)).all()
+    assert (rows[rows[:, 2] < n_tiles - 1][:, 3] == bn).all()
+    # balance in columns of work: a narrow tile never counts for less than half a full one (it still loads all of A)
+    cost = np.where(rows[:, 3] < bn, np.maximum(rows[:, 3], bn // 2), bn) / split_k
+    load = np.bincount(rows[:, 0], weights=cost, minlength=pairs)
+    used = load[load > 0]
+    assert used.max() - used.min() <= bn + 1e-9
+    # within a pair: full tiles first, narrow ones last
+    for p in range(pairs):
+        w = rows[rows[:, 0] == p][:, 3]
+        assert (np.diff(w) <= 0).all()
+
+
+def test_gemm_tail_split_schedule():
+    """Opt-in tail-only split-K: 384 tiles on 74 pairs = 5 full rounds + 14 tiles, each cut into 5 k parts that land on
+    70 different pairs; every whole tile and every (tail tile, part) appears exactly once."""
+    M, N, bn, pairs = 16384, 1152, 192, 74
+    units = (M // 256) * (N // bn)
+    tail, parts = units % pairs, pairs // (units % pairs)
+    rows = _schedule(M, N, 256, bn, 0, 1, pairs, tail_units=tail, tail_parts=parts)
+    assert (tail, parts) == (14, 5) and len(rows) == units - tail + tail * parts
+    per_pair = np.bincount(rows[:, 0], minlength=pairs)
+    assert per_pair.max() == 6 and per_pair.min() == 5
+    n_tiles = N // bn
+    tile = rows[:, 1] * n_tiles + rows[:, 2]
+    whole, split = rows[tile < units - tail], rows[tile >= units - tail]
+    assert len(whole) == units - tail and (whole[:, 4] == 0).all()
+    assert len({(t, k) for t, k in zip(tile[tile >= units - tail], split[:, 4])}) == tail * parts
+    assert set(split[:, 4]) == set(range(parts))
+    # the parts of the last round go to different pairs (one unit each): that is what makes the round short
+    assert len(set(split[:, 0])) == tail * parts
