@@ -69,6 +69,7 @@ SIGNATURES = {
     "ditb200_last_error": (C.c_char_p, []),
     "ditb200_set_gemm_dynamic": (_i, [_i]),
     "ditb200_debug_tile_schedule": (_i, [_i] * 9 + [C.c_void_p, _i]),
+    "ditb200_debug_gemm_plan": (_i, [_i] * 6 + [C.c_void_p]),
     "ditb200_sm_count": (_i, []),
     "ditb200_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _vp]),

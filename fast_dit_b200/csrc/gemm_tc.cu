@@ -1010,13 +1010,13 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
 // grows with the tile), 192 is within a few per cent, 128 costs ~30 %.  What decides between them for a given
 // shape is the length of the schedule: the chooser replays TileSched on the host for every legal width and takes
 // the smallest (max columns assigned to any CTA) / efficiency.
-static double sched_cost(int M, int N, int cg, int bn, int trans_w, int split_k) {
+static double sched_cost(int M, int N, int cg, int bn, int trans_w, int split_k, int sms) {
   const int tile_m = kBM * cg;
   const int m_tiles = (M + tile_m - 1) / tile_m;
   const int part = narrow_cols(N, bn, cg, trans_w);
   const int n_tiles = (N + bn - 1) / bn;
   const double eff = bn >= 256 ? 1.0 : (bn >= 192 ? 0.97 : 0.72);
-  int P = num_sms() / cg;
+  int P = sms / cg;
   const int units = m_tiles * n_tiles * split_k;
   if (P > units) P = units;
   if (split_k > 1 || part == 0) {
@@ -1038,7 +1038,7 @@ static double sched_cost(int M, int N, int cg, int bn, int trans_w, int split_k)
   return (double)mx / eff;
 }
 
-static void choose_tile(int M, int N, int K, int trans_w, int split_k, int* cg_out, int* bn_out) {
+static void choose_tile(int M, int N, int K, int trans_w, int split_k, int sms, int* cg_out, int* bn_out) {
   const int cg = (M > kBM) ? 2 : 1;
   *cg_out = cg;
   const int cand[3] = {256, 192, 128};
@@ -1048,13 +1048,23 @@ static void choose_tile(int M, int N, int K, int trans_w, int split_k, int* cg_o
     const int bn = cand[i];
     if (trans_w && (bn / cg) % 64 != 0) continue;   // MN-major B: 64-column boxes per CTA
     if (bn > 128 && N <= bn - 64) continue;          // a tile wider than the matrix buys nothing
-    double c = sched_cost(M, N, cg, bn, trans_w, split_k);
+    double c = sched_cost(M, N, cg, bn, trans_w, split_k, sms);
     // measured (N = 1152, M = 16384): with a long k loop an exact 192-wide cover beats 256 + a narrow column
     // (K = 4608: 134.1 vs 136.4 us); with a short one the shorter schedule of 256 + narrow wins (K = 1152: 39.5 vs 41.4)
     if (bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048 && K > 2048) c *= 0.8;
     if (c < best) best = c, best_bn = bn;
   }
   *bn_out = best_bn;
+}
+
+// Test hook: the tile shape the automatic chooser picks for a GEMM on a GPU with `sms` SMs: out = {cta_group,
+// tile_n, narrow last column}.  Host arithmetic only.
+extern "C" int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out) {
+  if (M <= 0 || N <= 0 || K <= 0 || split_k <= 0 || sms < 2 || !out) return DITB200_EINVAL;
+  int cg = 0, bn = 0;
+  choose_tile(M, N, K, trans_w, split_k, sms, &cg, &bn);
+  out[0] = cg, out[1] = bn, out[2] = narrow_cols(N, bn, cg, trans_w);
+  return 0;
 }
 
 int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
@@ -1092,7 +1102,7 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   int cg = a->cta_group, bn = a->tile_n;
   if (cg == 0 || bn == 0) {
     int acg, abn;
-    choose_tile(a->M, a->N, a->K, a->trans_w, split_k, &acg, &abn);
+    choose_tile(a->M, a->N, a->K, a->trans_w, split_k, num_sms(), &acg, &abn);
     if (cg == 0) cg = acg;
     if (bn == 0) bn = abn;
   }

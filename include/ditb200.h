@@ -82,6 +82,9 @@ int ditb200_set_gemm_dynamic(int on);
  * opt-in tail-only split-K (1 part = off).  Returns the number of rows, or -needed when cap is too small. */
 int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols, int split_k, int pairs,
                                 int tail_units, int tail_parts, int* rows, int cap);
+/* Test hook (host only): the tile the automatic chooser picks for an M x N x K GEMM on a GPU with `sms` SMs:
+ * out[3] = {cta_group, tile_n, width of the narrow last tile column (0: none)}. */
+int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out);
 
 /* ---------------------------------------------------------------- embedders */
 

@@ -168,3 +168,21 @@ def test_gemm_tail_split_schedule():
     assert set(split[:, 4]) == set(range(parts))
     # the parts of the last round go to different pairs (one unit each): that is what makes the round short
     assert len(set(split[:, 0])) == tail * parts
+
+
+@pytest.mark.parametrize("name,M,N,K,trans_w,expect", [
+    ("qkv", 16384, 3456, 1152, 0, (2, 256, 128)),
+    ("proj", 16384, 1152, 1152, 0, (2, 256, 128)),   # short k loop: 256 + narrow column (39.5 vs 41.4 us measured)
+    ("fc1", 16384, 4608, 1152, 0, (2, 256, 0)),
+    ("fc2", 16384, 1152, 4608, 0, (2, 192, 0)),      # long k loop: exact 192-wide cover (134.1 vs 136.4 us measured)
+    ("adaLN", 64, 66816, 1152, 0, (1, 256, 0)),       # M <= 128: single-CTA tiles
+    ("odd", 8200, 1160, 1152, 0, (2, 192, 16)),
+])
+def test_gemm_tile_chooser_pins_the_measured_choices(name, M, N, K, trans_w, expect):
+    """The automatic tile choice for the C3 shapes is the one the B200 measurements in DESIGN.md section 4 support."""
+    import ctypes
+    from fast_dit_b200 import _lib as L
+
+    out = (ctypes.c_int * 3)()
+    assert L.load().ditb200_debug_gemm_plan(M, N, K, trans_w, 1, 148, ctypes.cast(out, ctypes.c_void_p)) == 0
+    assert tuple(out) == expect, name
