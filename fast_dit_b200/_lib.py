@@ -70,6 +70,7 @@ SIGNATURES = {
     "ditb200_set_gemm_dynamic": (_i, [_i]),
     "ditb200_debug_tile_schedule": (_i, [_i] * 9 + [C.c_void_p, _i]),
     "ditb200_debug_gemm_plan": (_i, [_i] * 6 + [C.c_void_p]),
+    "ditb200_debug_attention_path": (_i, [_i] * 3),
     "ditb200_sm_count": (_i, []),
     "ditb200_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _vp]),

@@ -654,6 +654,15 @@ int launch_attn_bwd_tc(const void* qkv, const void* dout, const float* lse, cons
                        int H, int hd, cudaStream_t st);
 }  // namespace ditb200
 
+// Test hook (host only): which bf16 kernel family serves a (tokens per image, head dim) pair: 2 = tcgen05 with K/V
+// streamed in 128-key blocks (forward only), 1 = tcgen05 whole-row kernels, 0 = mma.sync flash kernels, -1 = rejected.
+extern "C" int ditb200_debug_attention_path(int T, int hd, int backward) {
+  if (T <= 0 || (hd != 64 && hd != 72 && !(hd == 80 && !backward && ditb200::attn_fwd_tc_supported(T, hd)))) return -1;
+  if (backward) return ditb200::attn_bwd_tc_supported(T, hd) ? 1 : 0;
+  if (!ditb200::attn_fwd_tc_supported(T, hd)) return 0;
+  return T > 256 ? 2 : 1;
+}
+
 extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
                                      int hd, void* stream) {
   DITB_REQUIRE(qkv && out, DITB200_EINVAL, "attention_fwd: null pointer");

@@ -85,6 +85,10 @@ int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols,
 /* Test hook (host only): the tile the automatic chooser picks for an M x N x K GEMM on a GPU with `sms` SMs:
  * out[3] = {cta_group, tile_n, width of the narrow last tile column (0: none)}. */
 int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out);
+/* Test hook (host only): kernel family that serves bf16 attention for T tokens per image and head dim hd:
+ * 2 = tcgen05, K/V streamed in 128-key blocks (forward, T = 512 / 768 / 1024 ...), 1 = tcgen05 whole-row kernels
+ * (T = 128 / 256 forward, T = 256 backward), 0 = mma.sync flash kernels (every other T), -1 = unsupported head dim. */
+int ditb200_debug_attention_path(int T, int hd, int backward);
 
 /* ---------------------------------------------------------------- embedders */
 

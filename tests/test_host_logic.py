@@ -186,3 +186,17 @@ def test_gemm_tile_chooser_pins_the_measured_choices(name, M, N, K, trans_w, exp
     out = (ctypes.c_int * 3)()
     assert L.load().ditb200_debug_gemm_plan(M, N, K, trans_w, 1, 148, ctypes.cast(out, ctypes.c_void_p)) == 0
     assert tuple(out) == expect, name
+
+
+@pytest.mark.parametrize("T,hd,backward,expect", [
+    (256, 72, 0, 1), (128, 72, 0, 1), (256, 64, 0, 1), (256, 80, 0, 1),       # whole-row tcgen05 forward
+    (1024, 72, 0, 2), (512, 64, 0, 2), (768, 72, 0, 2),                        # K/V-blocked tcgen05 forward (C5)
+    (64, 72, 0, 0), (100, 64, 0, 0), (300, 72, 0, 0),                          # every other T: mma.sync flash kernel
+    (256, 72, 1, 1), (256, 64, 1, 1), (1024, 72, 1, 0), (64, 72, 1, 0),        # backward
+    (256, 96, 0, -1), (64, 80, 0, -1), (256, 80, 1, -1),                       # head dims without a kernel
+])
+def test_attention_dispatch(T, hd, backward, expect):
+    """Which kernel family ditb200_attention_fwd / _bwd pick for (T, hd): DESIGN.md section 4's table, pinned."""
+    from fast_dit_b200 import _lib as L
+
+    assert L.load().ditb200_debug_attention_path(T, hd, backward) == expect
