@@ -17,7 +17,7 @@ case "$1" in
     if [ -z "$ref" ]; then
       python -m fast_dit_b200.build > /dev/null && cp $LIB ab/$name.so
     else
-      tmp=$(mktemp -d /tmp/ab_XXXX)
+      tmp=ab/_wt_$name; rm -rf "$tmp"; git worktree prune
       git worktree add --detach "$tmp" "$ref" > /dev/null
       (cd "$tmp" && python -m fast_dit_b200.build > /dev/null) && cp "$tmp/$LIB" ab/$name.so
       git worktree remove --force "$tmp"
