@@ -188,6 +188,9 @@ class GaussianDiffusion:
     def q_mean_variance(self, x_start, t):
         _unsupported("q_mean_variance")
 
+    def q_posterior_mean_variance(self, x_start, x_t, t):
+        _unsupported("q_posterior_mean_variance as a standalone op (GD:232-252; it is fused into the step kernel)")
+
     def q_sample(self, x_start, t, noise=None):
         """x_t ~ q(x_t | x_0) (GD:215-230)."""
         if noise is None:
