@@ -48,6 +48,9 @@ NVCC_FLAGS = [
     "-Xptxas",
     "-v",
 ]
+# measurement variants (tools/ab.sh): e.g. DITB200_NVCC_EXTRA=-DDITB200_PDL builds the programmatic-dependent-launch
+# variant of the hot kernels; part of the fingerprint, so switching it rebuilds
+NVCC_FLAGS += os.environ.get("DITB200_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

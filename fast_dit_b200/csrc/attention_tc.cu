@@ -121,6 +121,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  DITB_PDL_TRIGGER();  // PDL build variant only (common.cuh)
+  DITB_PDL_WAIT();
 
   if (warp == 8) {
     // ================================================================== TMA producer
@@ -1023,9 +1025,8 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
   }
   int grid = num_sms();
   if (grid > B * H) grid = B * H;
-  attn_fwd_tc_kernel<<<grid, kAtThreads, AttnSmem::kBytes, st>>>(mq0, mk0, mv0, mq1, mkv1,
-                                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd,
-                                                                 scale_log2e);
+  DITB_KLAUNCH(attn_fwd_tc_kernel, grid, kAtThreads, AttnSmem::kBytes, st, mq0, mk0, mv0, mq1, mkv1,
+               reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd, scale_log2e);
   DITB_LAUNCH_CHECK("attention_fwd(tcgen05)");
   return 0;
 }

@@ -40,6 +40,41 @@ EncodeTiledFn encode_tiled_fn();
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Programmatic dependent launch (build variant -DDITB200_PDL, off in the default build: the macros vanish and the
+// launches below are plain <<<>>>).  A kernel launched with the stream-serialization attribute may become resident
+// while its predecessor in the stream is still running; DITB_PDL_WAIT() blocks until that predecessor has completed
+// and its writes are visible, so it precedes every global access of the kernel (weights could go before it; kept
+// simple).  DITB_PDL_TRIGGER() lets the successor start launching; persistent
+// one-CTA-per-SM kernels call it at once (a successor cannot co-reside with them anyway and takes each SM as it is
+// vacated), multi-wave kernels never do (their exit is the trigger), so that an early successor cannot take their
+// registers.
+#ifdef DITB200_PDL
+#define DITB_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define DITB_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#else
+#define DITB_PDL_WAIT() ((void)0)
+#define DITB_PDL_TRIGGER() ((void)0)
+#endif
+
+// DITB_KLAUNCH((kernel<...>), grid, block, smem, stream, args...): plain launch in the default build; with the
+// stream-serialization attribute in the PDL variant (only for kernels that execute DITB_PDL_WAIT()).
+#ifdef DITB200_PDL
+template <typename... KArgs, typename... Args>
+static inline void launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in DITB_LAUNCH_CHECK
+}
+#define DITB_KLAUNCH(kern, g, b, s, st, ...) launch_dependent(kern, g, b, s, st, __VA_ARGS__)
+#else
+#define DITB_KLAUNCH(kern, g, b, s, st, ...) kern<<<g, b, s, st>>>(__VA_ARGS__)
+#endif
+
 // ---------------------------------------------------------------- device side
 #ifdef __CUDACC__
 

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           int mod_stride, void* __restrict__ out,
                                                           float* __restrict__ stats, int M, int T,
                                                           float eps) {
+  DITB_PDL_WAIT();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
     const float* __restrict__ x, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
     const float* __restrict__ shift, const float* __restrict__ scale, int mod_stride, float* __restrict__ x_out,
     void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps) {
+  DITB_PDL_WAIT();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -556,10 +558,10 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
 #define LN_CASE(NV)                                                                              \
   case NV * 128:                                                                                 \
     if (bf)                                                                                      \
-      ln_modulate_kernel<NV, true><<<grid, block, 0, st>>>(x, shift, scale, mod_stride, out,     \
+      DITB_KLAUNCH((ln_modulate_kernel<NV, true>), grid, block, 0, st, x, shift, scale, mod_stride, out,     \
                                                            stats, M, T, eps);                    \
     else                                                                                         \
-      ln_modulate_kernel<NV, false><<<grid, block, 0, st>>>(x, shift, scale, mod_stride, out,    \
+      DITB_KLAUNCH((ln_modulate_kernel<NV, false>), grid, block, 0, st, x, shift, scale, mod_stride, out,    \
                                                             stats, M, T, eps);                   \
     break;
   switch (D) {
@@ -599,10 +601,10 @@ extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const fl
 #define LNR_CASE(NV)                                                                                                  \
   case NV * 128:                                                                                                      \
     if (bf)                                                                                                           \
-      ln_modulate_resid_kernel<NV, true><<<grid, block, 0, st>>>(x, yb, gate, shift, scale, mod_stride, x_out, out,   \
+      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, true>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,   \
                                                                  stats, M, T, eps);                                   \
     else                                                                                                              \
-      ln_modulate_resid_kernel<NV, false><<<grid, block, 0, st>>>(x, yb, gate, shift, scale, mod_stride, x_out, out,  \
+      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, false>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,  \
                                                                   stats, M, T, eps);                                  \
     break;
   switch (D) {

@@ -613,6 +613,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if constexpr (kCG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // (PDL build variant only) barriers, TMEM and tensor maps are set up: let the next kernel's CTAs queue for this SM,
+  // then wait for the previous kernel's results before the first operand load / residual read / output write
+  DITB_PDL_TRIGGER();
+  DITB_PDL_WAIT();
 
   const int tile_m = kBM * kCG;
   const int k_blocks = (K + kBK - 1) / kBK;
@@ -956,13 +960,18 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCG * kMC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+#ifdef DITB200_PDL
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+#endif
   int clusters = num_sms() / (kCG * kMC);
   if constexpr (kMC > 1) {
     // clusters of 4 cannot tile every GPC: ask how many are co-resident (a persistent kernel must not queue any)

@@ -4,6 +4,8 @@
 #
 #   tools/ab.sh build <name> [<git-ref>]     here (CPU): build the library of <git-ref> (default: the working tree)
 #                                            into ab/<name>.so.  ab/ is git-ignored but travels with gpurun.
+#                                            DITB200_NVCC_EXTRA=-DDITB200_PDL tools/ab.sh build pdl  builds a flag variant
+#                                            (re-run `python -m fast_dit_b200.build` afterwards to restore the default library).
 #   tools/ab.sh run <nameA> <nameB> -- <cmd> on the GPU box: run <cmd> with each library in turn, twice (A B A B),
 #                                            e.g.  gpurun -- 'bash tools/ab.sh run old new -- python tools/tc_probe.py --no-cublas'
 # `run` leaves <nameB> installed as fast_dit_b200/lib/libditb200.so on that (throw-away) box only.
