@@ -200,3 +200,24 @@ def test_attention_dispatch(T, hd, backward, expect):
     from fast_dit_b200 import _lib as L
 
     assert L.load().ditb200_debug_attention_path(T, hd, backward) == expect
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) runs without a GPU and prints ONE JSON line with
+    the keys the driver reads; same metric / unit / workload naming as the GPU arm."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-images", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "img/s" and d["higher_is_better"] is True
+    assert "250-step" in d["metric"] and d["config"]["workload"].startswith("DiT-XL/2")
+    assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
