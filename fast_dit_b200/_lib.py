@@ -14,7 +14,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libditb200.so"
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_GATE_RESID, EPI_BIAS_SILU, EPI_MUL_DGELU = 0, 1, 2, 3, 4
 EPI_BIAS_GELU_DAUX, EPI_MUL_AUX = 5, 6
 GEMM_TCGEN05, GEMM_FP32 = 0, 1
@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("M", _i), ("N", _i), ("K", _i),
         ("epilogue", _i), ("out_dtype", _i), ("engine", _i), ("tile_n", _i), ("cta_group", _i),
         ("aux_out", _vp), ("aux_in", _vp), ("aux_dtype", _i), ("accumulate", _i), ("split_k", _i),
-        ("trans_a", _i), ("trans_w", _i),
+        ("trans_a", _i), ("trans_w", _i), ("dynamic_sched", _i),
     ]
 
 
@@ -67,8 +67,7 @@ SIGNATURES = {
     "ditb200_abi_version": (_i, []),
     "ditb200_init": (_i, [_i]),
     "ditb200_last_error": (C.c_char_p, []),
-    "ditb200_set_gemm_dynamic": (_i, [_i]),
-    "ditb200_debug_tile_schedule": (_i, [_i] * 9 + [C.c_void_p, _i]),
+    "ditb200_debug_tile_schedule": (_i, [_i] * 7 + [C.c_void_p, _i]),
     "ditb200_debug_gemm_plan": (_i, [_i] * 6 + [C.c_void_p]),
     "ditb200_debug_attention_path": (_i, [_i] * 3),
     "ditb200_sm_count": (_i, []),

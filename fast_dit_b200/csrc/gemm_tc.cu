@@ -55,10 +55,6 @@ struct EpiParams {
   int epilogue, out_bf16;
   int atomic;  // out += (f32 vector atomics): split-K partials and gradient accumulation
   int tma_store;  // bf16 output through smem staging + TMA store (tma_out is valid)
-  // tail-only split-K (see tail_exchange): the tiles of the ragged last round are cut along K
-  float* tail_ws;
-  int* tail_cnt;
-  int tail_units, tail_parts;
 };
 
 template <int kCG, int BN>
@@ -244,7 +240,6 @@ struct TileSched {
   // own unit and then cancels clusters that have not been launched yet and does their units.  SMs that become
   // free late (another kernel, e.g. an NCCL collective, held them) simply never receive work instead of owning a
   // fixed share of the schedule.  Responses land in a ring of kClcSlots 16-byte slots in every CTA of the pair.
-  int tail_first, tail_parts, tslot;  // tail-only split-K: first tail unit, parts per tail tile, slot of the current unit (-1: whole tile)
   int dyn, role, it;        // role: 0 = producer of the leader CTA (issues the queries), 1 = producer of the peer CTA, 2 = reader
   uint32_t clc_resp;        // shared address of the response ring
   uint64_t *clc_full, *clc_empty;
@@ -261,7 +256,6 @@ struct TileSched {
     q = part ? max(1, bn / max(part, bn / 2)) : 1;  // a narrow tile still loads the whole A tile: never cheaper than half a full one
     phase = 0, cur = p, end_a = 0;
     dyn = 0, role = 2, it = 0;
-    tail_first = num_units, tail_parts = 1, tslot = -1;
   }
   template <int kCG>
   __device__ __forceinline__ bool next_dyn(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
@@ -332,20 +326,6 @@ struct TileSched {
 #ifdef __CUDA_ARCH__
     if (dyn) return next_dyn<kCG>(bn, m_blk, n_blk, ncols, split);
 #endif
-    if (tail_parts > 1) {  // split_k == 1, no narrow column: whole tiles round-robin, then the tail tiles in parts
-      const int u = cur;
-      if (u >= tail_first + (num_units - tail_first) * tail_parts) return false;
-      cur += P;
-      int tile = u;
-      split = 0, tslot = -1;
-      if (u >= tail_first) {
-        tslot = (u - tail_first) / tail_parts;
-        split = (u - tail_first) - tslot * tail_parts;
-        tile = tail_first + tslot;
-      }
-      m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles, ncols = bn;
-      return true;
-    }
     if (split_k > 1 || part_cols == 0) {  // plain round-robin
       if (cur >= num_units) return false;
       const int tile = cur / split_k;
@@ -491,66 +471,6 @@ __device__ __forceinline__ void epi_tile_tma(const EpiParams& ep, const CUtensor
   }
 }
 
-__device__ __forceinline__ void tmem_st_32x32_acc(uint32_t taddr, const float (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
-      "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
-      "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
-      "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
-      : "memory");
-}
-
-// Tail-only split-K (opt-in, DITB200_GEMM_TAILSPLIT).  With U tiles on P CTA pairs the last round holds U mod P
-// tiles and leaves the other pairs idle (fc2 at C3: 14 of 74).  Those tiles are cut into `parts` k ranges, one
-// per pair.  Every epilogue warp dumps its share of the partial accumulator (f32, one 128-byte line per thread and
-// chunk) into the workspace; the CTA whose arrival completes the tile (atomic counter per tile and CTA rank: no
-// spinning, whoever comes last does the work) sums all parts in a fixed order, writes the sums back into its own
-// TMEM accumulator and runs the normal epilogue on them.  Returns true in that CTA.
-__device__ __noinline__ bool tail_exchange(float* ws, int* cnt, volatile uint32_t* flag, const uint32_t taddr0,
-                                           const int nch, const int slot, const int part, const int parts,
-                                           const int tile_rows, const int bn, const int row_in_tile, const int col_off,
-                                           const int cnt_idx, const bool elected) {
-  {
-    float* mine = ws + (((size_t)slot * parts + part) * tile_rows + row_in_tile) * bn + col_off;
-    for (int c = 0; c < nch; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(taddr0 + 32u * (uint32_t)c, v);
-      tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(mine + 32 * c);
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        __stcg(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                    __uint_as_float(v[4 * q + 3])));
-    }
-  }
-  __threadfence();
-  asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps of this CTA
-  if (elected) *flag = (uint32_t)atomicAdd(cnt + cnt_idx, 1);
-  asm volatile("bar.sync 1, 256;" ::: "memory");
-  if ((int)*flag != parts - 1) return false;
-  __threadfence();
-  for (int c = 0; c < nch; ++c) {
-    float acc[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) acc[q] = 0.f;
-    for (int j = 0; j < parts; ++j) {
-      const float4* src = reinterpret_cast<const float4*>(ws + (((size_t)slot * parts + j) * tile_rows + row_in_tile) * bn + col_off + 32 * c);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = __ldcg(src + q);
-        acc[4 * q] += t.x, acc[4 * q + 1] += t.y, acc[4 * q + 2] += t.z, acc[4 * q + 3] += t.w;
-      }
-    }
-    tmem_st_32x32_acc(taddr0 + 32u * (uint32_t)c, acc);
-  }
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  if (elected) cnt[cnt_idx] = 0;  // ready for the next launch
-  return true;
-}
-
 // kMC = CTA pairs per cluster.  With kMC == 2 (cluster of 4 CTAs) the two pairs work on vertically adjacent
 // 256-row tiles of the same tile column and SHARE the B tile: every CTA fetches one quarter of it and TMA
 // multicasts that quarter to the CTA holding the same B half in the other pair, so a 512 x 256 super-tile moves
@@ -579,7 +499,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* clc_full = bars + 2 * kStages + 5 + kEpiWarps;  // [kClcSlots] a launch-control response has landed
   uint64_t* clc_empty = clc_full + kClcSlots;               // [kClcSlots] (leader CTA) every reader is done with it
   uint8_t* clc_resp = reinterpret_cast<uint8_t*>(bars) + kBarBytes - 16 * kClcSlots;
-  volatile uint32_t* tail_flag = reinterpret_cast<volatile uint32_t*>(clc_resp - 16);  // tail_exchange: counter value seen by this CTA
   static_assert((2 * 8 + 5 + kEpiWarps + 2 * kClcSlots) * 8 + 16 + 16 * kClcSlots <= kBarBytes, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -623,8 +542,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int kb_per = (k_blocks + split_k - 1) / split_k;
   TileSched sched;
   sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC));
-  const int kb_per_tail = (k_blocks + ep.tail_parts - 1) / ep.tail_parts;
-  if (kMC == 1 && ep.tail_parts > 1) sched.tail_first = sched.num_units - ep.tail_units, sched.tail_parts = ep.tail_parts;
   if (kMC == 1 && dyn) {
     sched.dyn = 1, sched.role = (warp == 0) ? (leader ? 0 : 1) : 2;
     sched.clc_resp = smem_u32(clc_resp), sched.clc_full = clc_full, sched.clc_empty = clc_empty;
@@ -643,8 +560,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     while (sched.next<kCG>(BN, m_blk, n_blk, ncols, split)) {
       const int row_a = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM;
       const int row_b = n_blk * BN + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
-      const int kbp = sched.tslot >= 0 ? kb_per_tail : kb_per;
-      const int kb0 = split * kbp, kb1 = min(k_blocks, kb0 + kbp);
+      const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
@@ -702,8 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int iter = 0;
       for (; sched.next<kCG>(BN, m_blk, n_blk, ncols, split); ++iter) {
         const uint32_t idesc = idesc0 | ((uint32_t)(ncols >> 3) << 17);
-        const int kbp = sched.tslot >= 0 ? kb_per_tail : kb_per;
-        const int kb0 = split * kbp, kb1 = min(k_blocks, kb0 + kbp);
+        const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
@@ -766,7 +681,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      bool add_bias = ep.bias != nullptr && split == 0;
+      const bool add_bias = ep.bias != nullptr && split == 0;
       // the tile's 32-column chunks are split between the two warps of the lane quarter (narrow tiles too)
       // (TMA-store path: 64-column stores, so the first warp takes an even number of chunks)
       const int chunks = (ncols + 31) >> 5;
@@ -776,20 +691,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_off);
       const int colw = n_blk * BN + col_off;
       constexpr int NCH = BN / 64;
-      if (sched.tslot >= 0) {  // a k range of a last-round tile: only the CTA that completes the tile runs the epilogue
-        const bool reducer = tail_exchange(ep.tail_ws, ep.tail_cnt, tail_flag, taddr0, nch, sched.tslot, split, ep.tail_parts,
-                                           tile_m, BN, (int)cta_rank * kBM + quarter * 32 + lane, col_off,
-                                           sched.tslot * 2 + (int)cta_rank, warp == 2 && lane == 0);
-        if (!reducer) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (kCG == 1) mbar_arrive(&tmem_empty[acc]); else mbar_arrive_leader(&tmem_empty[acc], lead_rank);
-          }
-          continue;
-        }
-        add_bias = ep.bias != nullptr;
-      }
 #define EPI_CASE(E, O, A) epi_tile<E, O, A, NCH>(ep, taddr0, stg, lane, row0, colw, nch, M, N, add_bias)
       const bool has_aux = ep.aux_out != nullptr;
       const int omode = ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32);
@@ -872,27 +773,20 @@ static int narrow_cols(int N, int bn, int cg, int trans_w) {
   return np;
 }
 
-// Dynamic tile scheduling through cluster launch control (see TileSched).  Off by default: with the GPU to
-// itself the static longest-first schedule is as good and has no query latency; DataParallel turns it on so that
-// the backward GEMMs share the SMs with the overlapped NCCL all-reduce.
-static int g_dynamic_sched = getenv("DITB200_GEMM_DYNAMIC") != nullptr ? 1 : 0;
-extern "C" int ditb200_set_gemm_dynamic(int on) {
-  const int prev = g_dynamic_sched;
-  g_dynamic_sched = on ? 1 : 0;
-  return prev;
-}
+// Dynamic tile scheduling through cluster launch control (see TileSched) is requested per call
+// (ditb200_gemm_args::dynamic_sched).  Off by default: with the GPU to itself the static longest-first schedule is
+// as good and has no query latency.
 
 // Host replay of the static tile schedules (the very TileSched the kernel runs): for every CTA pair p the units it
 // would process, in order, as rows {p, m_blk, n_blk, ncols, k_part}.  Test hook: coverage and balance of the
 // schedule can be checked without a GPU (tests/test_host_logic.py).  Returns the number of rows (or -needed).
 extern "C" int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols, int split_k, int pairs,
-                                           int tail_units, int tail_parts, int* rows, int cap) {
+                                           int* rows, int cap) {
   if (M <= 0 || N <= 0 || tile_m <= 0 || bn <= 0 || split_k <= 0 || pairs <= 0 || part_cols < 0 || part_cols >= bn) return 0;
   int n = 0;
   for (int p = 0; p < pairs; ++p) {
     TileSched sc;
     sc.init(M, N, tile_m, bn, part_cols, split_k, pairs, p);
-    if (tail_parts > 1) sc.tail_first = sc.num_units - tail_units, sc.tail_parts = tail_parts;
     int m_blk = 0, n_blk = 0, ncols = 0, split = 0;
     while (sc.next<1>(bn, m_blk, n_blk, ncols, split)) {
       if (rows && n < cap) rows[5 * n] = p, rows[5 * n + 1] = m_blk, rows[5 * n + 2] = n_blk, rows[5 * n + 3] = ncols, rows[5 * n + 4] = split;
@@ -986,26 +880,8 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
     if (clusters > max_clusters) clusters = max_clusters;
   }
   if (clusters > units) clusters = units;
-  const int dyn = (kMC == 1 && g_dynamic_sched && units > clusters) ? 1 : 0;
+  const int dyn = (kMC == 1 && a->dynamic_sched && units > clusters) ? 1 : 0;
   const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
-  ep.tail_ws = nullptr, ep.tail_cnt = nullptr, ep.tail_units = 0, ep.tail_parts = 1;
-  static const bool tail_on = getenv("DITB200_GEMM_TAILSPLIT") != nullptr;  // opt-in (one shared workspace: one stream)
-  if (tail_on && kMC == 1 && !dyn && split_k == 1 && part == 0 && a->N % BN == 0 && units > clusters) {
-    const int rem = units % clusters, k_blocks = (a->K + kBK - 1) / kBK;
-    int parts = rem > 0 ? clusters / rem : 0;
-    if (parts > 8) parts = 8;
-    if (parts > k_blocks / 4) parts = k_blocks / 4;
-    if (rem > 0 && parts >= 2) {
-      static float* ws = nullptr;
-      static int* cnt = nullptr;
-      if (!ws) {  // 80 part-slots of 256 x 256 f32 (21 MB) and their arrival counters, once per process
-        if (cudaMalloc(&ws, (size_t)80 * 256 * 256 * sizeof(float)) != cudaSuccess || cudaMalloc(&cnt, 256 * sizeof(int)) != cudaSuccess ||
-            cudaMemset(cnt, 0, 256 * sizeof(int)) != cudaSuccess)
-          return check_cuda(cudaGetLastError(), "gemm_tc tail-split workspace");
-      }
-      if (rem * parts <= 80) ep.tail_ws = ws, ep.tail_cnt = cnt, ep.tail_units = rem, ep.tail_parts = parts;
-    }
-  }
   if (dyn) clusters = units;  // one cluster per unit; the running ones cancel and absorb the rest
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, taux, ep, a->M, a->N, a->K,

@@ -8,6 +8,7 @@ nothing falls back to torch ops.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -199,7 +200,7 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
                       _DT[out.dtype], engine, tile_n, cta_group,
                       _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
-                      int(trans_a), int(trans_w))
+                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
           meta=2.0 * M * N * K,
           tag=None if _PROFILE is None else
@@ -209,9 +210,16 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
     return out
 
 
+_GEMM_DYNAMIC = os.environ.get("DITB200_GEMM_DYNAMIC") is not None
+
+
 def set_gemm_dynamic(on: bool) -> bool:
-    """Switch the GEMMs' tile scheduler (include/ditb200.h: ditb200_set_gemm_dynamic); returns the previous setting."""
-    return bool(L.load().ditb200_set_gemm_dynamic(1 if on else 0))
+    """Tile scheduler requested by the following gemm() calls (ditb200_gemm_args.dynamic_sched: cluster launch
+    control instead of the static longest-first schedule); returns the previous setting.  Host-side default of this
+    module only: the library itself keeps no such state."""
+    global _GEMM_DYNAMIC
+    prev, _GEMM_DYNAMIC = _GEMM_DYNAMIC, bool(on)
+    return prev
 
 
 def cast_bf16(x, out=None):

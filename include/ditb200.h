@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DITB200_ABI_VERSION 2
+#define DITB200_ABI_VERSION 3
 
 #define DITB200_F32 0
 #define DITB200_BF16 1
@@ -71,17 +71,12 @@ int ditb200_abi_version(void);
 int ditb200_init(int device);
 const char* ditb200_last_error(void);
 int ditb200_sm_count(void);
-/* GEMM tile scheduling.  0 (default): every persistent CTA pair owns a fixed, longest-first share of the tiles.
- * 1: cluster launch control — the grid has one cluster per tile and running clusters cancel and absorb the ones
- * not yet launched, so SMs held by another kernel (the overlapped NCCL all-reduce of a data-parallel backward,
- * the role of torch DDP in train_options/train_original.py:149) never own tiles.  Returns the previous setting. */
-int ditb200_set_gemm_dynamic(int on);
 /* Test hook (host only, no GPU needed): replays the GEMM kernel's static tile schedule for `pairs` CTA pairs and
  * writes, for every pair in order, the units it would process as rows {pair, m_blk, n_blk, ncols, k_part} into
- * rows[5 * cap].  part_cols = width of the narrow last tile column (0: none); tail_units / tail_parts describe the
- * opt-in tail-only split-K (1 part = off).  Returns the number of rows, or -needed when cap is too small. */
+ * rows[5 * cap].  part_cols = width of the narrow last tile column (0: none).  Returns the number of rows, or -needed when cap
+ * is too small. */
 int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols, int split_k, int pairs,
-                                int tail_units, int tail_parts, int* rows, int cap);
+                                int* rows, int cap);
 /* Test hook (host only): the tile the automatic chooser picks for an M x N x K GEMM on a GPU with `sms` SMs:
  * out[3] = {cta_group, tile_n, width of the narrow last tile column (0: none)}. */
 int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out);
@@ -217,6 +212,11 @@ typedef struct ditb200_gemm_args {
   int trans_w;         /* TCGEN05: w is stored [K, N] row-major and read as an MN-major operand.
                           data gradient   dX[M,Kin]    = dY[M,Nout] . W[Nout,Kin]      -> trans_w
                           weight gradient dW[Nout,Kin] = dY[tokens,Nout]^T . X[tokens,Kin] -> trans_a + trans_w */
+  int dynamic_sched;   /* TCGEN05 tile scheduling.  0: every persistent CTA pair owns a fixed, longest-first share of
+                          the tiles.  1: cluster launch control — the grid has one cluster per tile and running
+                          clusters cancel and absorb the ones not yet launched, so SMs held by another kernel (the
+                          overlapped NCCL all-reduce of a data-parallel backward, the role of torch DDP in
+                          train_options/train_original.py:149) never own tiles.  Same results bit for bit. */
 } ditb200_gemm_args;
 
 /* out = epilogue(a · wᵀ).  Replaces, per DiTBlock: timm Attention.qkv (EPI_BIAS),

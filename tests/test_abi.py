@@ -21,7 +21,7 @@ def test_header_symbols_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in ditb200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
-    assert lib.ditb200_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.ditb200_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():

@@ -105,15 +105,14 @@ def test_model_refuses_cpu_inputs():
 
 
 # ------------------------------------------------------------------ GEMM tile schedule (host replay of the kernel's TileSched)
-def _schedule(M, N, tile_m, bn, part, split_k, pairs, tail_units=0, tail_parts=1):
+def _schedule(M, N, tile_m, bn, part, split_k, pairs):
     import ctypes
     from fast_dit_b200 import _lib as L
 
     lib = L.load()
     cap = 1 << 16
     buf = (ctypes.c_int * (5 * cap))()
-    n = lib.ditb200_debug_tile_schedule(M, N, tile_m, bn, part, split_k, pairs, tail_units, tail_parts,
-                                        ctypes.cast(buf, ctypes.c_void_p), cap)
+    n = lib.ditb200_debug_tile_schedule(M, N, tile_m, bn, part, split_k, pairs, ctypes.cast(buf, ctypes.c_void_p), cap)
     assert 0 < n <= cap
     return np.frombuffer(buf, dtype=np.int32)[: 5 * n].reshape(n, 5).copy()
 
@@ -148,26 +147,6 @@ def test_gemm_static_schedule_covers_every_tile_once(M, N, bn, part, split_k):
     for p in range(pairs):
         w = rows[rows[:, 0] == p][:, 3]
         assert (np.diff(w) <= 0).all()
-
-
-def test_gemm_tail_split_schedule():
-    """Opt-in tail-only split-K: 384 tiles on 74 pairs = 5 full rounds + 14 tiles, each cut into 5 k parts that land on
-    70 different pairs; every whole tile and every (tail tile, part) appears exactly once."""
-    M, N, bn, pairs = 16384, 1152, 192, 74
-    units = (M // 256) * (N // bn)
-    tail, parts = units % pairs, pairs // (units % pairs)
-    rows = _schedule(M, N, 256, bn, 0, 1, pairs, tail_units=tail, tail_parts=parts)
-    assert (tail, parts) == (14, 5) and len(rows) == units - tail + tail * parts
-    per_pair = np.bincount(rows[:, 0], minlength=pairs)
-    assert per_pair.max() == 6 and per_pair.min() == 5
-    n_tiles = N // bn
-    tile = rows[:, 1] * n_tiles + rows[:, 2]
-    whole, split = rows[tile < units - tail], rows[tile >= units - tail]
-    assert len(whole) == units - tail and (whole[:, 4] == 0).all()
-    assert len({(t, k) for t, k in zip(tile[tile >= units - tail], split[:, 4])}) == tail * parts
-    assert set(split[:, 4]) == set(range(parts))
-    # the parts of the last round go to different pairs (one unit each): that is what makes the round short
-    assert len(set(split[:, 0])) == tail * parts
 
 
 @pytest.mark.parametrize("name,M,N,K,trans_w,expect", [

@@ -222,7 +222,7 @@ def test_gemm_tcgen05_narrow_last_column_matches_full_tiles(ops, dev):
 @pytest.mark.parametrize("M,N,K,cg,bn", [(16384, 3456, 1152, 2, 256), (16384, 1152, 1152, 2, 192), (8200, 1160, 1152, 0, 0),
                                         (16384, 1152, 1152, 1, 256), (40000, 384, 64, 2, 128)])
 def test_gemm_dynamic_tile_scheduler_matches_static(ops, dev, M, N, K, cg, bn):
-    """ditb200_set_gemm_dynamic(1): one cluster per tile, running clusters cancel and absorb the pending ones through
+    """ditb200_gemm_args.dynamic_sched = 1: one cluster per tile, running clusters cancel and absorb the pending ones through
     cluster launch control.  Same tiles, same k order: the result must be bit-identical to the static schedule."""
     g = torch.Generator(device=dev).manual_seed(23)
     a = torch.randn(M, K, device=dev, generator=g).bfloat16()
