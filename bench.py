@@ -53,6 +53,17 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel as ncu measured them (dram__bytes_read.sum + dram__bytes_write.sum
+    of one `--set full` capture).  Not measurable inside a bench run, so the number is READ from the committed summary
+    of that capture (profiles/kernel_traffic.json names the capture file); absent -> null."""
+    p = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {})
+    except (OSError, ValueError):
+        return {}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -285,18 +296,21 @@ def run_ours(args):
             for _ in range(3):
                 diffusion.p_sample(model.forward_with_cfg, z_d, t_i, clip_denoised=False, model_kwargs=kw)
     summ = prof.summary()
+    by_shape = {tag: {"launches": v[0] // 3, "us_per_launch": v[1] / v[0] * 1e3, "tflops": v[2] / (v[1] * 1e-3) / 1e12}
+                for (kname, tag), v in sorted(prof.summary_by_tag().items(), key=lambda kv: -kv[1][1]) if kname == "gemm_tc"}
     step_ms_events = sum(v[1] for v in summ.values()) / 3
     g_n, g_ms, g_flops = summ["gemm_tc"]
     tf_peak, hbm_peak, which = peaks()
     achieved = g_flops / (g_ms * 1e-3) / 1e12
+    traffic = measured_traffic("gemm_tc")
     roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16, all DiT-block GEMMs + adaLN)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                 "peak_source": which,
                 # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest GEMM of the
                 # block (fc1, M=16384 N=4608 K=1152: 48.5 + 98.1 MB; algorithmic A + W + out = 199 MB, the rest stays
                 # in the 126 MB L2) -- profiles/r01_gemm_fc1_tma_full.md.  Tensor-bound kernel: context, not the bound.
-                "traffic": 146.6e6 if args.workload == "c3" else None,
-                "traffic_unit": "bytes per fc1 launch (ncu, profiles/r01_gemm_fc1_tma_full.md)",
+                "traffic": traffic.get("bytes") if args.workload == "c3" else None,
+                "traffic_unit": traffic.get("what"), "traffic_source": traffic.get("source"),
                 "launches_per_step": g_n // 3,
                 "avg_launch_us": g_ms / g_n * 1e3, "share_of_step": g_ms / 3 / step_ms_events}
     breakdown = {k: {"launches": v[0] // 3, "ms": v[1] / 3} for k, v in sorted(summ.items(), key=lambda kv: -kv[1][1])}
@@ -320,6 +334,7 @@ def run_ours(args):
         "mfu_bf16": {"value": mfu, "denominator_tflops": tf_peak, "flops_per_image_T": flops_img / 1e12},
         "fwd_img_per_s_per_gpu": 2 * n / (ms_per_step / T / 1e3),
         "kernel_breakdown_ms_per_denoise_step": breakdown,
+        "gemm_by_shape": by_shape,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -991,6 +991,8 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
     if (cg == 0) cg = acg;
     if (bn == 0) bn = abn;
   }
+  static const bool mc_auto = getenv("DITB200_GEMM_MC") != nullptr;  // measurement switch: multicast clusters where they fit exactly
+  if (mc_auto && a->cta_group == 0 && cg == 2 && bn == 256 && !a->trans_w && a->N % 256 == 0 && a->M % 512 == 0) cg = 4;
   DITB_REQUIRE(!a->trans_w || (bn / cg) % 64 == 0, DITB200_EINVAL,
                "gemm(tcgen05): trans_w needs tile_n / cta_group to be a multiple of 64 (got %d / %d)", bn, cg);
   if (cg == 4) {  // two CTA pairs per cluster sharing the B tile by TMA multicast (K-major B only)

@@ -18,6 +18,7 @@ epilogue; then the fused final layer (+unpatchify).  There is no PyTorch fallbac
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -27,6 +28,7 @@ from . import _lib as L
 from . import ops
 
 PRECISIONS = ("bf16", "fp32")
+_BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "0"))
 
 
 # --------------------------------------------------------------- parameter holders
@@ -264,18 +266,37 @@ class DiT(nn.Module):
         else:
             mod = ops.small_linear(c, sh["ada_w"], sh["ada_b"], silu_in=True)
         w = sh["w"]
+        # Where the gated residual update `x + gate * branch` (MO:120-121) runs.  0: in the epilogue of the GEMM that
+        # produces the branch (f32 stream read + written there).  1 / 2: the GEMM stores the bf16 branch by TMA and
+        # the update rides in front of the next LayerNorm (ln_modulate_resid), for proj + fc2 / for proj only
+        # (proj's k loop is too short to hide the f32 epilogue).  Chosen per build by measurement.
+        branch = _BRANCH_MODE if bf16 else 0
+        pend = None  # (branch output, gate) not yet folded into tok
         for i, blk in enumerate(self.blocks):
             m = mod[:, i * 6 * D:(i + 1) * 6 * D]
             sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * D:(j + 1) * D] for j in range(6))
-            h = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=act)
+            if pend is None:
+                h = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=act)
+            else:
+                _, h = ops.ln_modulate_resid(tok, pend[0], pend[1], sh1, sc1, T, out_dtype=act, x_out=tok)
+                pend = None
             qkv = ops.gemm(h, w[4 * i], blk.attn.qkv.bias)
             o = ops.attention(qkv, N, T, Hh, hd)
-            ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
-                     rows_per_gate=T)
-            h = ops.ln_modulate(tok, sh2, sc2, T, out_dtype=act)
+            if branch:
+                yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias)
+                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok)
+            else:
+                ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
+                         rows_per_gate=T)
+                h = ops.ln_modulate(tok, sh2, sc2, T, out_dtype=act)
             u = ops.gemm(h, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU)
-            ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g2,
-                     rows_per_gate=T)
+            if branch == 1:
+                pend = (ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias), g2)
+            else:
+                ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g2,
+                         rows_per_gate=T)
+        if pend is not None:  # last fc2 branch: plain update, the final layer normalises by itself
+            ops.ln_modulate_resid(tok, pend[0], pend[1], None, None, T, x_out=tok, want_out=False)
         mf = mod[:, self.depth * 6 * D:]
         fl = self.final_layer
         return ops.final_layer(tok, mf[:, :D], mf[:, D:], fl.linear.weight, fl.linear.bias, T, p, self.out_channels)

@@ -163,13 +163,15 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
     B = M // T
     _chk_contig(x, y)
     assert y.dtype == torch.bfloat16 and y.shape == x.shape
-    assert gate.stride(1) == 1 and shift.stride(1) == 1 and scale.stride(1) == 1
-    assert gate.stride(0) == shift.stride(0) == scale.stride(0)
+    assert gate.stride(1) == 1
+    if want_out:
+        assert shift.stride(1) == 1 and scale.stride(1) == 1 and gate.stride(0) == shift.stride(0) == scale.stride(0)
     if x_out is None:
         x_out = torch.empty_like(x)
     out = torch.empty((M, D), device=x.device, dtype=out_dtype) if want_out else None
-    _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift), _p(scale),
-          shift.stride(0), _p(x_out), _p(out), _DT[out_dtype], _p(stats), B, T, D, float(eps), _stream())
+    _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift if want_out else None),
+          _p(scale if want_out else None), gate.stride(0), _p(x_out), _p(out), _DT[out_dtype], _p(stats), B, T, D,
+          float(eps), _stream())
     return x_out, out
 
 

@@ -221,12 +221,12 @@ def test_attention_bwd_tcgen05_persistent(ops, dev, B, H, hd):
 
 
 # ---------------------------------------------------------------------------- the whole step
-def _oracle_grads(model_cpu, name, x, t, y, dout=None, loss_fn=None):
+def _oracle_grads(model_cpu, name, x, t, y, dout=None, loss_fn=None, drop_ids=None):
     from oracle import dit_oracle as O
 
     cfg = O.config_for(name, input_size=x.shape[-1])
     sd = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in model_cpu.state_dict(keep_vars=True).items()}
-    out = O.dit_forward(sd, cfg, x, t, y)
+    out = O.dit_forward(sd, cfg, x, t, y, drop_ids=drop_ids)
     if loss_fn is None:
         out.backward(dout)
     else:
@@ -234,7 +234,7 @@ def _oracle_grads(model_cpu, name, x, t, y, dout=None, loss_fn=None):
     return out.detach(), {k: v.grad for k, v in sd.items() if v.requires_grad}
 
 
-@pytest.mark.parametrize("name,B", [("DiT-S/2", 4), ("DiT-S/8", 5), ("DiT-B/4", 8)])
+@pytest.mark.parametrize("name,B", [("DiT-S/2", 4), ("DiT-S/8", 5), ("DiT-B/4", 8), ("DiT-XL/2", 2)])
 def test_model_gradients_against_oracle(dev, name, B):
     """Every parameter's gradient of <dout, DiT(x, t, y)> in bf16 against the fp32 CPU oracle's autograd.
     The reference's own bf16-autocast gradients sit ~1e-2 from its fp32 ones; bound per tensor 5e-2 and
@@ -311,6 +311,49 @@ def test_training_losses_step_against_oracle(dev):
         if p.requires_grad:
             num += float((p.grad.double().cpu() - ref[k].double()).pow(2).sum())
             den += float(ref[k].double().pow(2).sum())
+    assert math.sqrt(num / den) < 3e-2
+
+
+def test_xl2_training_step_train_mode_forced_drop(dev):
+    """The C4 model (DiT-XL/2: head dim 72, 28 blocks) in TRAIN mode through training_losses with the label-dropout
+    mask forced (models_original.py:79-87 draws it from torch.rand): loss terms and every parameter gradient against
+    the fp32 oracle's autograd with the same mask."""
+    from fast_dit_b200 import create_diffusion
+    from oracle.diffusion_oracle import DiffusionOracle
+    from util import build_product_model
+
+    name, B = "DiT-XL/2", 2
+    m = build_product_model(name, input_size=32, num_classes=1000, precision="bf16")
+    g = torch.Generator().manual_seed(14)
+    x0 = torch.randn(B, 4, 32, 32, generator=g)
+    noise = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.tensor([0, 731])
+    y = torch.randint(0, 1000, (B,), generator=g)
+    drop = torch.tensor([True, False])
+    do = DiffusionOracle("")
+    x_t = do.q_sample(x0, t, noise)
+
+    def loss_fn(out):
+        return do.training_losses(out, x0, x_t, t, noise)["loss"].mean()
+
+    ref_out, ref = _oracle_grads(m, name, x_t, do.map_t(t), y, loss_fn=loss_fn, drop_ids=drop)
+    ref_terms = do.training_losses(ref_out, x0, x_t, t, noise)
+    mc = m.cuda().train()
+    ye = mc.y_embedder
+    ye.token_drop = lambda labels, force_drop_ids=None: torch.where(drop.to(labels.device), ye.num_classes, labels)
+    d = create_diffusion("")
+    terms = d.training_losses(mc, x0.cuda(), t.cuda(), dict(y=y.cuda()), noise=noise.cuda())
+    for k in ("loss", "mse", "vb"):
+        assert rel_l2(terms[k], ref_terms[k]) < 2e-2, k
+    terms["loss"].mean().backward()
+    num = den = 0.0
+    for k, p in mc.named_parameters():
+        if p.requires_grad:
+            num += float((p.grad.double().cpu() - ref[k].double()).pow(2).sum())
+            den += float(ref[k].double().pow(2).sum())
+    # the dropped label's row of the embedding table receives gradient, the kept class row of sample 0 none
+    gt = mc.y_embedder.embedding_table.weight.grad
+    assert float(gt[1000].abs().sum()) > 0 and float(gt[int(y[0])].abs().sum()) == 0
     assert math.sqrt(num / den) < 3e-2
 
 
