@@ -20,7 +20,7 @@ EPI_BIAS_GELU_DAUX, EPI_MUL_AUX = 5, 6
 GEMM_TCGEN05, GEMM_FP32 = 0, 1
 MEAN_EPSILON, MEAN_START_X = 0, 1
 VAR_LEARNED_RANGE, VAR_LEARNED, VAR_FIXED = 0, 1, 2
-SAMPLER_ANCESTRAL, SAMPLER_DDIM = 0, 1
+SAMPLER_ANCESTRAL, SAMPLER_DDIM, SAMPLER_DDIM_REVERSE = 0, 1, 2
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -47,6 +47,7 @@ class StepArgs(C.Structure):
         ("B", _i), ("C", _i), ("HW", _i), ("num_timesteps", _i),
         ("mean_type", _i), ("var_type", _i), ("clip_denoised", _i),
         ("cfg_half", _i), ("n_cfg_ch", _i), ("cfg_scale", _f),
+        ("alphas_cumprod_next", _vp), ("mean_override", _vp),
     ]
 
 
@@ -59,6 +60,8 @@ class LossArgs(C.Structure):
         ("mse", _vp), ("vb", _vp), ("loss", _vp), ("grad_model_out", _vp),
         ("w_mse", _vp), ("w_vb", _vp), ("vb_scale", _f),
         ("B", _i), ("C", _i), ("HW", _i), ("num_timesteps", _i),
+        ("mean_type", _i), ("var_type", _i), ("fixed_log_var", _vp), ("clip_denoised", _i), ("vb_through_mean", _i),
+        ("pred_xstart", _vp), ("xstart_mse", _vp), ("eps_mse", _vp),
     ]
 
 
@@ -95,6 +98,8 @@ SIGNATURES = {
     "ditb200_p_sample_step": (_i, [C.POINTER(StepArgs), _vp]),
     "ditb200_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_training_losses": (_i, [C.POINTER(LossArgs), _vp]),
+    "ditb200_diffusion_affine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "ditb200_prior_bpd": (_i, [_vp, _f, _f, _vp, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

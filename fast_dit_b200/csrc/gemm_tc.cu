@@ -936,7 +936,8 @@ static void choose_tile(int M, int N, int K, int trans_w, int split_k, int sms, 
     double c = sched_cost(M, N, cg, bn, trans_w, split_k, sms);
     // measured (N = 1152, M = 16384): with a long k loop an exact 192-wide cover beats 256 + a narrow column
     // (K = 4608: 134.1 vs 136.4 us); with a short one the shorter schedule of 256 + narrow wins (K = 1152: 39.5 vs 41.4)
-    if (bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048 && K > 2048) c *= 0.8;
+    static const bool no192 = getenv("DITB200_GEMM_NO192") != nullptr;  // measurement switch
+    if (!no192 && bn == 192 && N % 192 == 0 && N % 256 != 0 && N < 2048 && K > 2048) c *= 0.8;
     if (c < best) best = c, best_bn = bn;
   }
   *bn_out = best_bn;

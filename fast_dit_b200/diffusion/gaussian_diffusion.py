@@ -233,7 +233,13 @@ class GaussianDiffusion:
             "log_betas": up(np.log(self.betas)),
             "alphas_cumprod": up(self.alphas_cumprod),
             "alphas_cumprod_prev": up(self.alphas_cumprod_prev),
+            "alphas_cumprod_next": up(self.alphas_cumprod_next),
+            "one_minus_alphas_cumprod": up(1.0 - self.alphas_cumprod),
+            "log_one_minus_alphas_cumprod": up(self.log_one_minus_alphas_cumprod),
+            "posterior_variance": up(self.posterior_variance),
         }
+        # condition_score's (1 - alpha_bar).sqrt() is f32 arithmetic on the gathered f32 alpha_bar (GD:365-368)
+        tab["sqrt_one_minus_alphas_cumprod_f32"] = th.sqrt(1 - tab["alphas_cumprod"])
         vt = self.model_var_type
         if vt == ModelVarType.LEARNED_RANGE:
             tab["min_log"], tab["max_log"] = tab["posterior_log_variance_clipped"], tab["log_betas"]
@@ -254,11 +260,31 @@ class GaussianDiffusion:
         return mean, var
 
     # ------------------------------------------------------------------ forward process
+    @staticmethod
+    def _f32(*xs):
+        return [x.float().contiguous() for x in xs]
+
+    def _wrap_model(self, model):
+        return model  # SpacedDiffusion maps spaced step indices to original timesteps here (RS:89-97)
+
     def q_mean_variance(self, x_start, t):
-        _unsupported("q_mean_variance")
+        """q(x_t | x_0): (mean, variance, log_variance), each of x_start's shape (GD:203-213)."""
+        (x,) = self._f32(x_start)
+        t = t.long().contiguous()
+        tab = self._tables(x.device)
+        return (ops.diffusion_affine(t, a=x, ta=tab["sqrt_alphas_cumprod"]),
+                ops.diffusion_affine(t, ta=tab["one_minus_alphas_cumprod"], like=x),
+                ops.diffusion_affine(t, ta=tab["log_one_minus_alphas_cumprod"], like=x))
 
     def q_posterior_mean_variance(self, x_start, x_t, t):
-        _unsupported("q_posterior_mean_variance as a standalone op (GD:232-252; it is fused into the step kernel)")
+        """q(x_{t-1} | x_t, x_0): (mean, variance, clipped log-variance) (GD:232-252)."""
+        assert x_start.shape == x_t.shape
+        x0, xt = self._f32(x_start, x_t)
+        t = t.long().contiguous()
+        tab = self._tables(xt.device)
+        return (ops.diffusion_affine(t, a=x0, ta=tab["posterior_mean_coef1"], b=xt, tb=tab["posterior_mean_coef2"]),
+                ops.diffusion_affine(t, ta=tab["posterior_variance"], like=xt),
+                ops.diffusion_affine(t, ta=tab["posterior_log_variance_clipped"], like=xt))
 
     def q_sample(self, x_start, t, noise=None):
         """x_t ~ q(x_t | x_0) (GD:215-230)."""
@@ -287,7 +313,7 @@ class GaussianDiffusion:
         return model(x, t, **kw), 0, 1.0
 
     def _step(self, model, x, t, *, clip_denoised, denoised_fn, model_kwargs, noise, want, sampler=L.SAMPLER_ANCESTRAL,
-              eta=0.0):
+              eta=0.0, cond_fn=None):
         B, C = x.shape[:2]
         assert t.shape == (B,)
         x = x.float().contiguous()
@@ -310,11 +336,31 @@ class GaussianDiffusion:
             edited = denoised_fn(first["pred_xstart"]).float()
             out = th.cat([edited, first["log_variance"]], dim=1).contiguous()
             mean_t, var_t, cfg_half = L.MEAN_START_X, L.VAR_LEARNED, 0
-        if callable(noise):  # drawn after the model call, where the reference draws it (GD:410)
-            noise = self._noise_override if self._noise_override is not None else noise(x).float().contiguous()
+
+        def draw(nz):  # drawn after the model call, where the reference draws it (GD:410)
+            if callable(nz):
+                return self._noise_override if self._noise_override is not None else nz(x).float().contiguous()
+            return nz
+
+        mean_override = None
+        if cond_fn is not None:
+            # classifier guidance: the unconditioned distribution first, the user's gradient, then the update from
+            # the conditioned mean (p_sample, GD:398-401) or the conditioned x0 (DDIM, GD:536-537 / 584-585)
+            pm = ops.p_sample_step(out, x, None, t, tab, mean_type=mean_t, var_type=var_t, clip_denoised=clip_denoised,
+                                   cfg_half=cfg_half, n_cfg_ch=3, cfg_scale=cfg_scale,
+                                   want=("mean", "variance", "log_variance", "pred_xstart"))
+            if sampler == L.SAMPLER_ANCESTRAL:
+                noise = draw(noise)  # p_sample draws before it calls cond_fn
+                mean_override = self.condition_mean(cond_fn, pm, x, t, model_kwargs=model_kwargs)
+                pred = pm["pred_xstart"]
+            else:
+                pred = self.condition_score(cond_fn, pm, x, t, model_kwargs=model_kwargs)["pred_xstart"]
+            out = th.cat([pred, pm["log_variance"]], dim=1).contiguous()
+            mean_t, var_t, cfg_half, clip_denoised = L.MEAN_START_X, L.VAR_LEARNED, 0, False
+        noise = draw(noise)
         res = ops.p_sample_step(out, x, noise, t, tab, mean_type=mean_t, var_type=var_t,
                                 clip_denoised=clip_denoised, cfg_half=cfg_half, n_cfg_ch=3, cfg_scale=cfg_scale,
-                                want=want, sampler=sampler, eta=eta)
+                                want=want, sampler=sampler, eta=eta, mean_override=mean_override)
         res["extra"] = extra
         return res
 
@@ -326,23 +372,44 @@ class GaussianDiffusion:
         return {k: r[k] for k in ("mean", "variance", "log_variance", "pred_xstart", "extra")}
 
     def _predict_xstart_from_eps(self, x_t, t, eps):
-        _unsupported("_predict_xstart_from_eps as a standalone op (it is fused into the step kernel)")
+        """sqrt(1/ab) x_t - sqrt(1/ab - 1) eps (GD:334-339)."""
+        assert x_t.shape == eps.shape
+        xt, e = self._f32(x_t, eps)
+        tab = self._tables(xt.device)
+        return ops.diffusion_affine(t.long().contiguous(), a=xt, ta=tab["sqrt_recip_alphas_cumprod"], b=e,
+                                    tb=tab["sqrt_recipm1_alphas_cumprod"], subtract=True)
 
     def _predict_eps_from_xstart(self, x_t, t, pred_xstart):
-        _unsupported("_predict_eps_from_xstart as a standalone op (it is fused into the DDIM step kernel)")
+        """(sqrt(1/ab) x_t - x0) / sqrt(1/ab - 1) (GD:341-344)."""
+        xt, p = self._f32(x_t, pred_xstart)
+        tab = self._tables(xt.device)
+        return ops.diffusion_affine(t.long().contiguous(), a=xt, ta=tab["sqrt_recip_alphas_cumprod"], b=p, subtract=True,
+                                    td=tab["sqrt_recipm1_alphas_cumprod"])
 
     def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
-        _unsupported("classifier guidance (cond_fn)")
+        """Classifier guidance after Sohl-Dickstein et al.: mean + variance * grad log p(y|x) (GD:346-357)."""
+        gradient = cond_fn(x, t, **(model_kwargs or {}))
+        mean, var, grad = self._f32(p_mean_var["mean"], p_mean_var["variance"], gradient)
+        return ops.diffusion_affine(t.long().contiguous(), a=mean, b=var, b2=grad)
 
     def condition_score(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
-        _unsupported("classifier guidance (cond_fn)")
+        """Classifier guidance after Song et al.: eps -= sqrt(1 - ab) * grad, then x0 and the posterior mean are
+        re-derived from the conditioned eps (GD:359-374)."""
+        (xf,) = self._f32(x)
+        tl = t.long().contiguous()
+        tab = self._tables(xf.device)
+        eps = self._predict_eps_from_xstart(xf, tl, p_mean_var["pred_xstart"])
+        (grad,) = self._f32(cond_fn(x, t, **(model_kwargs or {})))
+        eps = ops.diffusion_affine(tl, a=eps, b=grad, tb=tab["sqrt_one_minus_alphas_cumprod_f32"], subtract=True)
+        out = dict(p_mean_var)
+        out["pred_xstart"] = self._predict_xstart_from_eps(xf, tl, eps)
+        out["mean"], _, _ = self.q_posterior_mean_variance(x_start=out["pred_xstart"], x_t=xf, t=tl)
+        return out
 
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None):
         """Ancestral step x_t -> x_{t-1} (GD:376-417): {'sample', 'pred_xstart'}."""
-        if cond_fn is not None:
-            _unsupported("classifier guidance (cond_fn)")
         r = self._step(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs,
-                       noise=lambda z: _randn_like(z), want=("sample", "pred_xstart"))
+                       noise=lambda z: _randn_like(z), want=("sample", "pred_xstart"), cond_fn=cond_fn)
         return {"sample": r["sample"], "pred_xstart": r["pred_xstart"]}
 
     # ------------------------------------------------------------- graph-captured loops
@@ -441,16 +508,18 @@ class GaussianDiffusion:
     def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                     eta=0.0):
         """DDIM step (GD:513-560)."""
-        if cond_fn is not None:
-            _unsupported("classifier guidance (cond_fn)")
         r = self._step(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs,
                        noise=lambda z: _randn_like(z), want=("sample", "pred_xstart"), sampler=L.SAMPLER_DDIM,
-                       eta=float(eta))
+                       eta=float(eta), cond_fn=cond_fn)
         return {"sample": r["sample"], "pred_xstart": r["pred_xstart"]}
 
     def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None,
                             model_kwargs=None, eta=0.0):
-        _unsupported("ddim_reverse_sample")
+        """x_t -> x_{t+1} along the deterministic DDIM ODE (GD:562-598); draws no noise."""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        r = self._step(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs,
+                       noise=None, want=("sample", "pred_xstart"), sampler=L.SAMPLER_DDIM_REVERSE, cond_fn=cond_fn)
+        return {"sample": r["sample"], "pred_xstart": r["pred_xstart"]}
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0):
@@ -477,34 +546,89 @@ class GaussianDiffusion:
         yield from self._loop(step, model, shape, noise, device, progress)
 
     # ------------------------------------------------------------------------ training
+    def _loss_terms(self, model_output, x_start, x_t, noise, t, *, clip_denoised, vb_through_mean, vb_scale,
+                    want_pred=False):
+        """(loss = mse + vb, mse, vb, pred_xstart) from the loss kernel, differentiable wrt model_output."""
+        from ..autograd import diffusion_loss
+
+        if self.model_mean_type == ModelMeanType.PREVIOUS_X:
+            _unsupported("ModelMeanType.PREVIOUS_X (the reference's own p_mean_variance does not handle it either, GD:317-322)")
+        B, C = x_t.shape[:2]
+        learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
+        assert model_output.shape == (B, C * 2 if learned else C, *x_t.shape[2:])
+        mean_t, var_t = self._kernel_types()
+        return diffusion_loss(model_output, x_start, x_t, noise, t, self._tables(x_t.device), vb_scale,
+                              mean_type=mean_t, var_type=var_t, clip_denoised=clip_denoised,
+                              vb_through_mean=vb_through_mean, want_pred=want_pred)
+
     def _vb_terms_bpd(self, model, x_start, x_t, t, clip_denoised=True, model_kwargs=None):
-        _unsupported("_vb_terms_bpd as a standalone op (the MSE-family loss kernel computes it fused)")
+        """One term of the variational bound in bits (GD:682-713): {'output': KL(q || p), or the decoder NLL where
+        t == 0; 'pred_xstart'}.  Differentiable wrt the model output (mean and variance channels)."""
+        x0, xt = self._f32(x_start, x_t)
+        t = t.long().contiguous()
+        out = self._wrap_model(model)(xt, t, **(model_kwargs or {}))
+        if isinstance(out, tuple):
+            out = out[0]
+        _, _, vb, pred = self._loss_terms(out, x0, xt, xt, t, clip_denoised=clip_denoised, vb_through_mean=True,
+                                          vb_scale=1.0, want_pred=True)
+        return {"output": vb, "pred_xstart": pred}
 
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None):
-        """Per-sample training loss terms (GD:715-787) for the MSE loss family with a learned
-        variance range — what create_diffusion("") builds and train.py uses: {'loss','mse','vb'}."""
+        """Per-sample training loss terms (GD:715-787).  MSE family: {'loss', 'mse'} plus 'vb' when the variance
+        is learned (what create_diffusion("") builds and train.py uses); KL family: {'loss'}."""
         if model_kwargs is None:
             model_kwargs = {}
-        if self.loss_type not in (LossType.MSE, LossType.RESCALED_MSE):
-            _unsupported(f"loss_type {self.loss_type}")
-        if self.model_var_type != ModelVarType.LEARNED_RANGE or self.model_mean_type != ModelMeanType.EPSILON:
-            _unsupported("training_losses for anything but EPSILON + LEARNED_RANGE")
         if noise is None:
             noise = _randn_like(x_start)
-        x_start = x_start.float().contiguous()
-        noise = noise.float().contiguous()
+        x_start, noise = self._f32(x_start, noise)
         t = t.long().contiguous()
         x_t = self.q_sample(x_start, t, noise=noise)
-        model_output = model(x_t, t, **model_kwargs)
-        B, C = x_t.shape[:2]
-        assert model_output.shape == (B, C * 2, *x_t.shape[2:])
-        from ..autograd import diffusion_loss
+        model_output = self._wrap_model(model)(x_t, t, **model_kwargs)
+        if self.loss_type.is_vb():  # GD:735-746
+            scale = float(self.num_timesteps) if self.loss_type == LossType.RESCALED_KL else 1.0
+            _, _, vb, _ = self._loss_terms(model_output, x_start, x_t, noise, t, clip_denoised=False,
+                                           vb_through_mean=True, vb_scale=scale)
+            return {"loss": vb}
+        learned = self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE)
         vb_scale = self.num_timesteps / 1000.0 if self.loss_type == LossType.RESCALED_MSE else 1.0
-        loss, mse, vb = diffusion_loss(model_output, x_start, x_t, noise, t, self._tables(x_t.device), vb_scale)
-        return {"loss": loss, "mse": mse, "vb": vb}
+        loss, mse, vb, _ = self._loss_terms(model_output, x_start, x_t, noise, t, clip_denoised=False,
+                                            vb_through_mean=False, vb_scale=vb_scale)
+        if learned:
+            return {"loss": loss, "mse": mse, "vb": vb}
+        return {"loss": mse, "mse": mse}  # fixed variance: no VLB term (GD:779-783)
 
     def _prior_bpd(self, x_start):
-        _unsupported("_prior_bpd")
+        """KL(q(x_T | x_0) || N(0, I)) in bits per dimension (GD:789-803)."""
+        (x0,) = self._f32(x_start)
+        return ops.prior_bpd(x0, float(np.float32(self.sqrt_alphas_cumprod[-1])),
+                             float(np.float32(self.log_one_minus_alphas_cumprod[-1])))
 
     def calc_bpd_loop(self, model, x_start, clip_denoised=True, model_kwargs=None):
-        _unsupported("calc_bpd_loop")
+        """The whole variational bound in bits per dimension (GD:805-858): {'total_bpd', 'prior_bpd', 'vb' [N, T],
+        'xstart_mse' [N, T], 'mse' [N, T]}.  Per timestep: one noise draw, q_sample, the model, and ONE loss kernel
+        that yields the VLB term, the x0 error and the eps error together."""
+        (x0,) = self._f32(x_start)
+        device, B = x0.device, x0.shape[0]
+        wrapped = self._wrap_model(model)
+        mean_t, var_t = self._kernel_types()
+        if self.model_mean_type == ModelMeanType.PREVIOUS_X:
+            _unsupported("ModelMeanType.PREVIOUS_X")
+        tab = self._tables(device)
+        vb, xstart_mse, mse = [], [], []
+        for step in list(range(self.num_timesteps))[::-1]:
+            t_batch = th.full((B,), step, device=device, dtype=th.long)
+            noise = _randn_like(x0).float().contiguous()
+            x_t = self.q_sample(x0, t_batch, noise=noise)
+            with th.no_grad():
+                out = wrapped(x_t, t_batch, **(model_kwargs or {}))
+                if isinstance(out, tuple):
+                    out = out[0]
+                r = ops.training_losses(out.float().contiguous(), x0, x_t, noise, t_batch, tab, 1.0, mean_type=mean_t,
+                                        var_type=var_t, clip_denoised=clip_denoised, want_pred=False, want_bpd_terms=True)
+            vb.append(r["vb"])
+            xstart_mse.append(r["xstart_mse"])
+            mse.append(r["eps_mse"])
+        vb, xstart_mse, mse = (th.stack(v, dim=1) for v in (vb, xstart_mse, mse))
+        prior_bpd = self._prior_bpd(x0)
+        return {"total_bpd": vb.sum(dim=1) + prior_bpd, "prior_bpd": prior_bpd, "vb": vb, "xstart_mse": xstart_mse,
+                "mse": mse}

@@ -84,6 +84,9 @@ class SpacedDiffusion(GaussianDiffusion):
     def training_losses(self, model, *args, **kwargs):
         return super().training_losses(self._wrap_model(model), *args, **kwargs)
 
+    def ddim_reverse_sample(self, model, *args, **kwargs):
+        return super().ddim_reverse_sample(self._wrap_model(model), *args, **kwargs)
+
     def condition_mean(self, cond_fn, *args, **kwargs):
         return super().condition_mean(self._wrap_model(cond_fn), *args, **kwargs)
 

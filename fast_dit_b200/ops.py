@@ -283,10 +283,11 @@ def cfg_combine(raw, n_cfg_ch: int, cfg_scale: float, out=None):
 
 def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_denoised,
                   cfg_half=0, n_cfg_ch=0, cfg_scale=1.0, want=("sample", "pred_xstart"),
-                  sampler=L.SAMPLER_ANCESTRAL, eta=0.0):
-    """One fused ancestral step.  tables: dict of f32 device tensors (see diffusion/)."""
+                  sampler=L.SAMPLER_ANCESTRAL, eta=0.0, mean_override=None):
+    """One fused sampling step (ancestral, DDIM or reversed DDIM).  tables: dict of f32 device tensors (see
+    diffusion/); mean_override: the classifier-guided mean of condition_mean (ancestral only)."""
     lib = _lib_for(x)
-    _chk_contig(model_out, x, noise, t)
+    _chk_contig(model_out, x, noise, t, mean_override)
     B, Cc = x.shape[0], x.shape[1]
     HW = x[0, 0].numel()
     outs = {k: torch.empty_like(x) for k in want}
@@ -301,7 +302,8 @@ def p_sample_step(model_out, x, noise, t, tables, *, mean_type, var_type, clip_d
         _p(outs.get("variance")), _p(tables.get("var_table")), _p(tables.get("alphas_cumprod")), _p(tables.get("alphas_cumprod_prev")),
         float(eta), int(sampler),
         B, Cc, HW, int(tables["posterior_mean_coef1"].numel()),
-        mean_type, var_type, int(bool(clip_denoised)), int(cfg_half), int(n_cfg_ch), float(cfg_scale))
+        mean_type, var_type, int(bool(clip_denoised)), int(cfg_half), int(n_cfg_ch), float(cfg_scale),
+        _p(tables.get("alphas_cumprod_next")), _p(mean_override))
     _call("p_sample_step", lib.ditb200_p_sample_step, C.byref(args), _stream())
     return outs
 
@@ -316,9 +318,12 @@ def q_sample(x0, noise, t, sqrt_ac, sqrt_1mac):
     return out
 
 
-def training_losses(model_out, x0, x_t, noise, t, tables, vb_scale: float = 1.0, w_mse=None, w_vb=None):
+def training_losses(model_out, x0, x_t, noise, t, tables, vb_scale: float = 1.0, w_mse=None, w_vb=None, *,
+                    mean_type=L.MEAN_EPSILON, var_type=L.VAR_LEARNED_RANGE, clip_denoised=False, vb_through_mean=False,
+                    want_pred=False, want_bpd_terms=False):
     """mse / vb / loss per sample; with w_mse and w_vb ([B] upstream gradients) also the gradient
-    with respect to model_out."""
+    with respect to model_out.  vb_through_mean: the VLB term's gradient reaches the mean channels (KL losses).
+    want_pred / want_bpd_terms: also return the x0 prediction / calc_bpd_loop's xstart_mse and eps mse."""
     lib = _lib_for(x0)
     _chk_contig(model_out, x0, x_t, noise, t, w_mse, w_vb)
     B, Cc = x0.shape[0], x0.shape[1]
@@ -328,15 +333,44 @@ def training_losses(model_out, x0, x_t, noise, t, tables, vb_scale: float = 1.0,
     vb = torch.empty_like(mse)
     loss = torch.empty_like(mse)
     grad = torch.empty_like(model_out) if w_mse is not None else None
+    pred = torch.empty_like(x0) if want_pred else None
+    xs_mse = torch.empty_like(mse) if want_bpd_terms else None
+    eps_mse = torch.empty_like(mse) if want_bpd_terms else None
     args = L.LossArgs(
         _p(model_out), _p(x0), _p(x_t), _p(noise), _p(t),
         _p(tables["sqrt_recip_alphas_cumprod"]), _p(tables["sqrt_recipm1_alphas_cumprod"]),
         _p(tables["posterior_mean_coef1"]), _p(tables["posterior_mean_coef2"]),
         _p(tables["posterior_log_variance_clipped"]), _p(tables["log_betas"]),
         _p(mse), _p(vb), _p(loss), _p(grad), _p(w_mse), _p(w_vb), float(vb_scale), B, Cc, HW,
-        int(tables["posterior_mean_coef1"].numel()))
+        int(tables["posterior_mean_coef1"].numel()),
+        int(mean_type), int(var_type), _p(tables.get("min_log") if var_type == L.VAR_FIXED else None),
+        int(bool(clip_denoised)), int(bool(vb_through_mean)), _p(pred), _p(xs_mse), _p(eps_mse))
     _call("training_losses", lib.ditb200_training_losses, C.byref(args), _stream())
-    return {"mse": mse, "vb": vb, "loss": loss, "grad_model_out": grad}
+    return {"mse": mse, "vb": vb, "loss": loss, "grad_model_out": grad, "pred_xstart": pred, "xstart_mse": xs_mse,
+            "eps_mse": eps_mse}
+
+
+def diffusion_affine(t, *, a=None, ta=None, b=None, tb=None, b2=None, td=None, subtract=False, like=None):
+    """out = (ta[t] * a (+|-) tb[t] * b * b2) / td[t] per sample (include/ditb200.h: ditb200_diffusion_affine)."""
+    ref = a if a is not None else (b if b is not None else like)
+    lib = _lib_for(ref)
+    _chk_contig(a, b, b2, t)
+    B = ref.shape[0]
+    n = ref[0].numel()
+    out = torch.empty(ref.shape, device=ref.device, dtype=torch.float32)
+    table = ta if ta is not None else (tb if tb is not None else td)
+    _call("diffusion_affine", lib.ditb200_diffusion_affine, _p(a), _p(b), _p(b2), _p(t), _p(ta), _p(tb), _p(td),
+          int(bool(subtract)), _p(out), B, n, int(table.numel()) if table is not None else 1, _stream())
+    return out
+
+
+def prior_bpd(x0, coef_mean: float, log_var: float):
+    lib = _lib_for(x0)
+    _chk_contig(x0)
+    out = torch.empty(x0.shape[0], device=x0.device, dtype=torch.float32)
+    _call("prior_bpd", lib.ditb200_prior_bpd, _p(x0), float(coef_mean), float(log_var), _p(out), x0.shape[0],
+          x0[0].numel(), _stream())
+    return out
 
 
 # ------------------------------------------------------------------- backward pass

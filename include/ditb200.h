@@ -64,6 +64,7 @@ extern "C" {
 /* update rule of ditb200_p_sample_step */
 #define DITB200_SAMPLER_ANCESTRAL 0 /* p_sample  (gaussian_diffusion.py:376-417) */
 #define DITB200_SAMPLER_DDIM 1      /* ddim_sample (gaussian_diffusion.py:513-560) */
+#define DITB200_SAMPLER_DDIM_REVERSE 2 /* ddim_reverse_sample, x_t -> x_{t+1} (gaussian_diffusion.py:562-598) */
 
 int ditb200_abi_version(void);
 /* One-off per process+device: resolves the driver's tensor-map encoder, reads
@@ -317,6 +318,12 @@ typedef struct ditb200_step_args {
                         combine of ditb200_cfg_combine is applied on the fly */
   int n_cfg_ch;
   float cfg_scale;
+  /* DDIM_REVERSE only: alphas_cumprod_next table (gaussian_diffusion.py:171) */
+  const float* alphas_cumprod_next;
+  /* ANCESTRAL only, optional [B, C, HW]: use this mean instead of the posterior mean in the update — the
+   * classifier-guided mean of condition_mean (gaussian_diffusion.py:346-357, 398-401); the `mean` output
+   * still reports the unconditioned one */
+  const float* mean_override;
 } ditb200_step_args;
 
 /* One sampling step x_t → x_{t-1}, fully fused.
@@ -324,6 +331,7 @@ typedef struct ditb200_step_args {
  * q_posterior_mean_variance + the update in p_sample
  * (diffusion/gaussian_diffusion.py:285-293, 320-323, 334-339, 238-241, 410-416),
  * or the DDIM update of ddim_sample (:541-560) when sampler == DITB200_SAMPLER_DDIM,
+ * or the reversed DDIM ODE step of ddim_reverse_sample (:583-598) when sampler == DITB200_SAMPLER_DDIM_REVERSE,
  * and, with cfg_half > 0, forward_with_cfg's combine (models_original.py:258-266). */
 int ditb200_p_sample_step(const ditb200_step_args* args, void* stream);
 
@@ -332,8 +340,27 @@ int ditb200_q_sample(const float* x0, const float* noise, const int64_t* t,
                      const float* sqrt_alphas_cumprod, const float* sqrt_one_minus_alphas_cumprod,
                      float* x_t, int B, int CHW, int num_timesteps, void* stream);
 
+/* Per-sample affine combination with coefficients gathered from f32 schedule tables:
+ *     out[b, i] = ( ta[t_b] * a[b, i]  (+|-)  tb[t_b] * b[b, i] * b2[b, i] ) / td[t_b]
+ * Any factor may be absent: ta == NULL -> coefficient 1, a == NULL -> the first term is ta[t_b] itself (a
+ * broadcast of the table: _extract_into_tensor, gaussian_diffusion.py:861-873); b == NULL -> no second term;
+ * tb == NULL -> coefficient 1; b2 == NULL -> factor 1; td == NULL -> no division; subtract != 0 -> minus.
+ * Every product / sum is rounded separately in the order written (no FMA contraction), so the results are the
+ * reference's eager f32 values bit for bit.  Serves the standalone helpers of GaussianDiffusion:
+ * q_mean_variance (:203-213), q_posterior_mean_variance (:232-252), _predict_xstart_from_eps (:334-339),
+ * _predict_eps_from_xstart (:341-344), condition_mean (:346-357) and the eps update of condition_score (:367-368).
+ * t int64 [B]; tables f32 [num_timesteps]; tensors f32 [B, n]. */
+int ditb200_diffusion_affine(const float* a, const float* b, const float* b2, const int64_t* t, const float* ta,
+                             const float* tb, const float* td, int subtract, float* out, int B, int n,
+                             int num_timesteps, void* stream);
+
+/* _prior_bpd (gaussian_diffusion.py:789-803): per sample, mean over elements of
+ * KL( N(sqrt_ac[T-1] * x0, 1 - ac[T-1]) || N(0, 1) ) in bits.  coef_mean = sqrt_alphas_cumprod[T-1],
+ * log_var = log_one_minus_alphas_cumprod[T-1] (f32 values of the tables).  x0 [B, n] -> out [B]. */
+int ditb200_prior_bpd(const float* x0, float coef_mean, float log_var, float* out, int B, int n, void* stream);
+
 typedef struct ditb200_loss_args {
-  const float* model_out; /* [B, 2C, HW] f32 */
+  const float* model_out; /* [B, 2C, HW] f32 ([B, C, HW] with DITB200_VAR_FIXED) */
   const float* x0;        /* [B, C, HW] */
   const float* x_t;       /* [B, C, HW] */
   const float* noise;     /* [B, C, HW] */
@@ -350,14 +377,26 @@ typedef struct ditb200_loss_args {
   float* grad_model_out;  /* [B, 2C, HW] out or NULL: d(sum_b w_mse[b]*mse[b] + w_vb[b]*vb[b]) / d model_out */
   const float* w_mse;     /* [B] upstream gradients of mse (+loss); required with grad_model_out */
   const float* w_vb;      /* [B] upstream gradients of vb (+loss) */
-  float vb_scale;         /* 1, or num_timesteps/1000 for RESCALED_MSE (gaussian_diffusion.py:766-769) */
+  float vb_scale;         /* 1, or num_timesteps/1000 for RESCALED_MSE (gaussian_diffusion.py:766-769);
+                             num_timesteps for RESCALED_KL (:745-746) */
   int B, C, HW, num_timesteps;
+  /* --- everything below is optional; all-zero reproduces the MSE + LEARNED_RANGE + EPSILON loss --- */
+  int mean_type;          /* DITB200_MEAN_*: what model_out's first C channels predict */
+  int var_type;           /* DITB200_VAR_*; FIXED reads fixed_log_var */
+  const float* fixed_log_var; /* VAR_FIXED: the model log-variance table (gaussian_diffusion.py:295-308) */
+  int clip_denoised;      /* clamp the x0 prediction to [-1, 1] before the posterior mean (_vb_terms_bpd's
+                             clip_denoised; training passes False, calc_bpd_loop True) */
+  int vb_through_mean;    /* 0: the VLB term sees a detached mean (MSE family, :755-758).  1: its gradient also
+                             flows into the mean channels — the KL / RESCALED_KL loss (:735-746) */
+  float* pred_xstart;     /* [B, C, HW] out or NULL: the (clipped) x0 prediction (_vb_terms_bpd's 'pred_xstart') */
+  float* xstart_mse;      /* [B] out or NULL: mean((pred_xstart - x0)^2)                     (calc_bpd_loop :842) */
+  float* eps_mse;         /* [B] out or NULL: mean((eps(pred_xstart) - noise)^2)             (calc_bpd_loop :843-844) */
 } ditb200_loss_args;
 
-/* training_losses for MSE + LEARNED_RANGE + EPSILON (what create_diffusion("")
- * builds): mse, vb (KL or decoder NLL at t == 0, in bits), loss, and the gradient
- * wrt the model output, one kernel with warp-shuffle row reductions.
- * Replaces gaussian_diffusion.py:747-781, 682-713 and diffusion_utils.py:10-36,62-88. */
+/* training_losses / _vb_terms_bpd: mse, vb (KL or decoder NLL at t == 0, in bits), loss = mse + vb, and the
+ * gradient wrt the model output, one kernel with warp-shuffle row reductions.  The default (zeroed optional
+ * fields) is MSE + LEARNED_RANGE + EPSILON, what create_diffusion("") builds.
+ * Replaces gaussian_diffusion.py:735-781, 682-713, 836-844 and diffusion_utils.py:10-36,62-88. */
 int ditb200_training_losses(const ditb200_loss_args* args, void* stream);
 
 #ifdef __cplusplus

@@ -159,6 +159,106 @@ def gen_diffusion_kat():
     print("diffusion_kat", len(d))
 
 
+def cond_fn_fixture(x, t, **kw):
+    """Stand-in for grad log p(y | x): exactly-rounded IEEE f32 ops only, so CPU and GPU evaluate it identically."""
+    return x * 0.5 - 0.25 + (t.float() * 0.001).view(-1, 1, 1, 1)
+
+
+API_CASES = [
+    ("lr250", "250", {}, [249, 0, 17, 100]),
+    ("lr1000", "", {}, [0, 637, 999, 1]),
+    ("fl250", "250", {"learn_sigma": False}, [249, 0, 17, 100]),
+    ("fs250", "250", {"learn_sigma": False, "sigma_small": True}, [249, 0, 17, 100]),
+    ("x0_250", "250", {"predict_xstart": True}, [249, 0, 17, 100]),
+    ("cos100", "100", {"noise_schedule": "squaredcos_cap_v2"}, [99, 0, 50, 1]),
+]
+
+
+def gen_diffusion_api():
+    """The rest of GaussianDiffusion's surface: standalone q/p helpers, classifier guidance (cond_fn) through
+    p_sample / ddim_sample, ddim_reverse_sample, the KL loss family, _vb_terms_bpd, _prior_bpd, calc_bpd_loop, and
+    the MSE loss for fixed-variance / x0-predicting models."""
+    d = {}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 16, 16, generator=g)
+    out8 = torch.randn(4, 8, 16, 16, generator=g) * 0.5
+    noise = torch.randn(4, 4, 16, 16, generator=g)
+    x0 = torch.randn(4, 4, 16, 16, generator=g).clamp(-1.2, 1.2)
+    w = torch.tensor([0.25, 1.0, -0.5, 2.0])
+    d.update(x=x.numpy(), out8=out8.numpy(), noise=noise.numpy(), x0=x0.numpy(), w=w.numpy())
+    orig = ref_gd.th.randn_like
+    ref_gd.th.randn_like = lambda z: noise.clone()
+    try:
+        for tag, spec, kw, t in API_CASES:
+            df = ref_diffusion.create_diffusion(spec, **kw)
+            tt = torch.tensor(t)
+            mo = out8 if kw.get("learn_sigma", True) else out8[:, :4].contiguous()
+            stub = lambda *a, **k: mo  # noqa: E731
+            d[tag + "|t"] = np.array(t)
+            for k, v in zip(("mean", "variance", "log_variance"), df.q_mean_variance(x0, tt)):
+                d[f"{tag}|qmv.{k}"] = v.numpy()
+            for k, v in zip(("mean", "variance", "log_variance"), df.q_posterior_mean_variance(x0, x, tt)):
+                d[f"{tag}|qpost.{k}"] = v.numpy()
+            d[tag + "|x0_from_eps"] = df._predict_xstart_from_eps(x, tt, out8[:, :4]).numpy()
+            d[tag + "|eps_from_x0"] = df._predict_eps_from_xstart(x, tt, x0).numpy()
+            for clip in (False, True):
+                c = f"{tag}|clip{int(clip)}|"
+                r = df.p_sample(stub, x, tt, clip_denoised=clip, cond_fn=cond_fn_fixture, model_kwargs={})
+                d[c + "p_sample_cond"], d[c + "p_sample_cond.pred"] = r["sample"].numpy(), r["pred_xstart"].numpy()
+                r = df.ddim_sample(stub, x, tt, clip_denoised=clip, cond_fn=cond_fn_fixture, model_kwargs={}, eta=0.3)
+                d[c + "ddim_cond"], d[c + "ddim_cond.pred"] = r["sample"].numpy(), r["pred_xstart"].numpy()
+                r = df.ddim_reverse_sample(stub, x, tt, clip_denoised=clip)
+                d[c + "ddim_rev"], d[c + "ddim_rev.pred"] = r["sample"].numpy(), r["pred_xstart"].numpy()
+                r = df.ddim_reverse_sample(stub, x, tt, clip_denoised=clip, cond_fn=cond_fn_fixture, model_kwargs={})
+                d[c + "ddim_rev_cond"] = r["sample"].numpy()
+                x_t = df.q_sample(x0, tt, noise=noise)
+                r = df._vb_terms_bpd(stub, x0, x_t, tt, clip_denoised=clip)
+                d[c + "vb.output"], d[c + "vb.pred"] = r["output"].numpy(), r["pred_xstart"].numpy()
+            d[tag + "|prior_bpd"] = df._prior_bpd(x0).numpy()
+            # MSE-family loss and gradient for every mean / variance type
+            mo_g = mo.clone().requires_grad_(True)
+            tl = df.training_losses(lambda *a, **k: mo_g, x0, tt, noise=noise)
+            (tl["loss"] * w).sum().backward()
+            for k in tl:
+                d[f"{tag}|mse.{k}"] = tl[k].detach().numpy()
+            d[tag + "|mse.grad"] = mo_g.grad.numpy()
+            # KL family (GD:735-746): RESCALED_KL is what create_diffusion(use_kl=True) builds; KL by loss_type
+            for lt in ("RESCALED_KL", "KL"):
+                dk = ref_diffusion.create_diffusion(spec, use_kl=True, **kw)
+                dk.loss_type = getattr(ref_gd.LossType, lt)
+                mo_g = mo.clone().requires_grad_(True)
+                tl = dk.training_losses(lambda *a, **k: mo_g, x0, tt, noise=noise)
+                assert set(tl) == {"loss"}
+                (tl["loss"] * w).sum().backward()
+                d[f"{tag}|{lt}.loss"] = tl["loss"].detach().numpy()
+                d[f"{tag}|{lt}.grad"] = mo_g.grad.numpy()
+    finally:
+        ref_gd.th.randn_like = orig
+    # calc_bpd_loop over a 10-step process; every step's noise from its own seeded generator
+    for tag, kw in [("bpd10", {}), ("bpd10_fl", {"learn_sigma": False})]:
+        df = ref_diffusion.create_diffusion("10", **kw)
+        mo = out8 if kw.get("learn_sigma", True) else out8[:, :4].contiguous()
+        step = {"i": 0}
+
+        def seeded(zl):
+            gg = torch.Generator().manual_seed(500 + step["i"])
+            step["i"] += 1
+            return torch.randn(zl.shape, generator=gg)
+
+        ref_gd.th.randn_like = seeded
+        try:
+            for clip in (True, False):
+                step["i"] = 0
+                r = df.calc_bpd_loop(lambda xx, ts, **k: mo * (1.0 + ts.float().view(-1, 1, 1, 1) * 0.001), x0,
+                                     clip_denoised=clip, model_kwargs={})
+                for k, v in r.items():
+                    d[f"{tag}|clip{int(clip)}|{k}"] = v.numpy()
+        finally:
+            ref_gd.th.randn_like = orig
+    np.savez_compressed(os.path.join(OUT, "diffusion_api.npz"), **d)
+    print("diffusion_api", len(d))
+
+
 def gen_sample_loop(model):
     """BASELINE.json configs[0]: DiT-S/2, 10-step CFG-4.0 sampling (n=2 kept images, batch 4 with the
     null-class half), every step's noise drawn from its own seeded CPU generator."""
@@ -193,7 +293,11 @@ def gen_sample_loop(model):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the fixture added in round 2
+        gen_diffusion_api()
+        sys.exit(0)
     gen_tables()
+    gen_diffusion_api()
     gen_tiny()
     gen_diffusion_kat()
     s2 = gen_seeded("DiT-S/2", 32, 4, "s2_seed0")
