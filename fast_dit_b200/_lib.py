@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("M", _i), ("N", _i), ("K", _i),
         ("epilogue", _i), ("out_dtype", _i), ("engine", _i), ("tile_n", _i), ("cta_group", _i),
         ("aux_out", _vp), ("aux_in", _vp), ("aux_dtype", _i), ("accumulate", _i), ("split_k", _i),
-        ("trans_a", _i), ("trans_w", _i), ("dynamic_sched", _i),
+        ("trans_a", _i), ("trans_w", _i), ("dynamic_sched", _i), ("reverse_m", _i),
     ]
 
 
@@ -78,8 +78,8 @@ SIGNATURES = {
     "ditb200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "ditb200_small_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_label_embed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
-    "ditb200_ln_modulate_resid": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _f, _vp]),
+    "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp]),
+    "ditb200_ln_modulate_resid": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp]),
     "ditb200_ln_modulate_bwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ditb200_gate_resid_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "ditb200_colsum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
@@ -90,7 +90,7 @@ SIGNATURES = {
     "ditb200_gemm": (_i, [C.POINTER(GemmArgs), _vp]),
     "ditb200_cast_bf16": (_i, [_vp, _vp, _sz, _vp]),
     "ditb200_silu_cast": (_i, [_vp, _vp, _i, _sz, _vp]),
-    "ditb200_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ditb200_attention_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_attention_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ditb200_final_layer": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "ditb200_adamw_ema": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _f, _f, _f, _f, _f, _i, _f, _vp]),

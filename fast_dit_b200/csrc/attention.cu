@@ -648,7 +648,7 @@ static int launch_attn_bf16(const void* qkv, void* out, float* lse, int B, int T
 namespace ditb200 {
 // attention_tc.cu: tcgen05 / TMEM forward for T in {128, 256}, head dim 64..80
 bool attn_fwd_tc_supported(int T, int hd);
-int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st);
+int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, int reverse, cudaStream_t st);
 bool attn_bwd_tc_supported(int T, int hd);
 int launch_attn_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv, int B, int T,
                        int H, int hd, cudaStream_t st);
@@ -664,7 +664,7 @@ extern "C" int ditb200_debug_attention_path(int T, int hd, int backward) {
 }
 
 extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
-                                     int hd, void* stream) {
+                                     int hd, int reverse, void* stream) {
   DITB_REQUIRE(qkv && out, DITB200_EINVAL, "attention_fwd: null pointer");
   DITB_REQUIRE(B > 0 && T > 0 && H > 0 && hd > 0, DITB200_EINVAL, "attention_fwd: bad shape");
   DITB_REQUIRE(B <= 65535 && H <= 65535, DITB200_EINVAL, "attention_fwd: B, H must fit a grid dimension");
@@ -672,7 +672,7 @@ extern "C" int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int
   if (dtype == DITB200_BF16) {
     DITB_REQUIRE(aligned16(qkv) && aligned16(out), DITB200_EALIGN, "attention_fwd: misaligned pointer");
     static const bool legacy = getenv("DITB200_ATTN_MMA_SYNC") != nullptr;  // measurement switch
-    if (!legacy && attn_fwd_tc_supported(T, hd)) return launch_attn_fwd_tc(qkv, out, lse, B, T, H, hd, st);
+    if (!legacy && attn_fwd_tc_supported(T, hd)) return launch_attn_fwd_tc(qkv, out, lse, B, T, H, hd, reverse, st);
     if (hd == 64) return launch_attn_bf16<64>(qkv, out, lse, B, T, H, st);
     if (hd == 72) return launch_attn_bf16<72>(qkv, out, lse, B, T, H, st);
     set_error("attention_fwd(bf16): head dim %d not supported (64, 72)", hd);

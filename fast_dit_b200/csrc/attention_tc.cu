@@ -87,7 +87,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
                    const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_q1,
                    const __grid_constant__ CUtensorMap map_kv1, __nv_bfloat16* __restrict__ out,
                    float* __restrict__ lse, const int B, const int T, const int H, const int hd,
-                   const float scale_log2e) {
+                   const float scale_log2e, const int reverse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem::oBars);
@@ -130,7 +130,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
     const uint32_t kv_bytes = (uint32_t)(2 * T * 128 + (has_c1 ? 2 * T * 32 : 0));
     int it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int b = w / H, h = w - b * H;
+      const int wi = reverse ? n_items - 1 - w : w;  // last-first: start on what the QKV GEMM wrote last (L2)
+      const int b = wi / H, h = wi - b * H;
       const int stage = it & 1;
       const uint32_t kvpar = (it >> 1) & 1, par = it & 1;
       const int tok0 = b * T;
@@ -232,7 +233,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const int nch = T / 32;  // 32-key chunks of the score row
       int it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        const int b = w / H, h = w - b * H;
+        const int wi = reverse ? n_items - 1 - w : w;
+        const int b = wi / H, h = wi - b * H;
         const uint32_t par = it & 1;
         mbar_wait(&s_full[t], par);
         tcgen05_fence_after();
@@ -988,7 +990,7 @@ bool attn_fwd_tc_supported(int T, int hd) {
   return (T == 128 || T == 256 || (T > 256 && T % 256 == 0)) && hd % 8 == 0 && hd >= 64 && hd <= 80;
 }
 
-int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, cudaStream_t st) {
+int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int H, int hd, int reverse, cudaStream_t st) {
   DITB_REQUIRE(is_initialised(), DITB200_ENOINIT, "attention: ditb200_init() has not been called");
   CUtensorMap mq0, mk0, mv0, mq1, mkv1;
   const uint64_t tokens = (uint64_t)B * T;
@@ -1026,7 +1028,7 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
   int grid = num_sms();
   if (grid > B * H) grid = B * H;
   DITB_KLAUNCH(attn_fwd_tc_kernel, grid, kAtThreads, AttnSmem::kBytes, st, mq0, mk0, mv0, mq1, mkv1,
-               reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd, scale_log2e);
+               reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd, scale_log2e, reverse ? 1 : 0);
   DITB_LAUNCH_CHECK("attention_fwd(tcgen05)");
   return 0;
 }

@@ -18,12 +18,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
                                                           const float* __restrict__ scale,
                                                           int mod_stride, void* __restrict__ out,
                                                           float* __restrict__ stats, int M, int T,
-                                                          float eps) {
+                                                          float eps, int reverse) {
   DITB_PDL_WAIT();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
+  if (reverse) row = M - 1 - row;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   float4 v[NV];
 #pragma unroll
@@ -74,12 +75,13 @@ template <int NV, bool kOutBf16>
 __global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
     const float* __restrict__ x, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
     const float* __restrict__ shift, const float* __restrict__ scale, int mod_stride, float* __restrict__ x_out,
-    void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps) {
+    void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps, int reverse) {
   DITB_PDL_WAIT();
   constexpr int D = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  int row = blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= M) return;
+  if (reverse) row = M - 1 - row;
   const int b = row / T;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   const uint2* yr = reinterpret_cast<const uint2*>(y + (size_t)row * D);
@@ -559,10 +561,10 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
   case NV * 128:                                                                                 \
     if (bf)                                                                                      \
       DITB_KLAUNCH((ln_modulate_kernel<NV, true>), grid, block, 0, st, x, shift, scale, mod_stride, out,     \
-                                                           stats, M, T, eps);                    \
+                                                           stats, M, T, eps, reverse);           \
     else                                                                                         \
       DITB_KLAUNCH((ln_modulate_kernel<NV, false>), grid, block, 0, st, x, shift, scale, mod_stride, out,    \
-                                                            stats, M, T, eps);                   \
+                                                            stats, M, T, eps, reverse);          \
     break;
   switch (D) {
     LN_CASE(3)
@@ -584,7 +586,7 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
 
 extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
                                          const float* scale, int mod_stride, float* x_out, void* out, int out_dtype,
-                                         float* stats, int B, int T, int D, float eps, void* stream) {
+                                         float* stats, int B, int T, int D, float eps, int reverse, void* stream) {
   DITB_REQUIRE(x && y && gate && x_out, DITB200_EINVAL, "ln_modulate_resid: null pointer");
   DITB_REQUIRE(out == nullptr || (shift && scale), DITB200_EINVAL, "ln_modulate_resid: out needs shift and scale");
   DITB_REQUIRE(B > 0 && T > 0 && (D == 384 || D == 768 || D == 1024 || D == 1152), DITB200_EINVAL,
@@ -602,10 +604,10 @@ extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const fl
   case NV * 128:                                                                                                      \
     if (bf)                                                                                                           \
       DITB_KLAUNCH((ln_modulate_resid_kernel<NV, true>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,   \
-                                                                 stats, M, T, eps);                                   \
+                                                                 stats, M, T, eps, reverse);                          \
     else                                                                                                              \
       DITB_KLAUNCH((ln_modulate_resid_kernel<NV, false>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,  \
-                                                                  stats, M, T, eps);                                  \
+                                                                  stats, M, T, eps, reverse);                         \
     break;
   switch (D) {
     LNR_CASE(3)

@@ -235,6 +235,7 @@ struct TileSched {
   int n_full, part_cols;    // full tile columns, width of the narrow last column (0 = none)
   int F, H, r, q;           // full tiles, narrow tiles, light-CTA threshold, narrow tiles per light CTA
   int split_k, n_tiles, num_units;
+  int m_last;               // >= 0: tile rows are visited last-first (m_blk -> m_last - m_blk); -1: first-first
   int phase, cur, end_a;
   // dynamic mode (cluster launch control): the grid has one cluster per work unit; a running cluster finishes its
   // own unit and then cancels clusters that have not been launched yet and does their units.  SMs that become
@@ -244,9 +245,11 @@ struct TileSched {
   uint32_t clc_resp;        // shared address of the response ring
   uint64_t *clc_full, *clc_empty;
 
-  __host__ __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair) {
+  __host__ __device__ __forceinline__ void init(int M, int N, int tile_m, int bn, int part, int split, int pairs, int pair,
+                                               int reverse_m = 0) {
     P = pairs, p = pair, split_k = split;
     const int m_tiles = (M + tile_m - 1) / tile_m;
+    m_last = reverse_m ? m_tiles - 1 : -1;
     n_tiles = (N + bn - 1) / bn;
     num_units = m_tiles * n_tiles * split_k;
     part_cols = part;
@@ -320,9 +323,17 @@ struct TileSched {
     }
     return true;
   }
-  // next unit of this CTA: tile coordinates, tile width in columns, k-split index
+  // next unit of this CTA: tile coordinates, tile width in columns, k-split index.  With m_last >= 0 the same
+  // schedule runs over the tile rows mirrored: the kernel then starts with the rows its producer kernel wrote LAST
+  // (still in L2) and finishes with the rows the next kernel, traversing the other way, reads first.
   template <int kCG>
   __host__ __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
+    const bool ok = next_unmirrored<kCG>(bn, m_blk, n_blk, ncols, split);
+    if (ok && m_last >= 0) m_blk = m_last - m_blk;
+    return ok;
+  }
+  template <int kCG>
+  __host__ __device__ __forceinline__ bool next_unmirrored(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
 #ifdef __CUDA_ARCH__
     if (dyn) return next_dyn<kCG>(bn, m_blk, n_blk, ncols, split);
 #endif
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
-               const int split_k, const int part_cols, const int dyn) {
+               const int split_k, const int part_cols, const int dyn, const int reverse_m) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -541,7 +552,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int k_blocks = (K + kBK - 1) / kBK;
   const int kb_per = (k_blocks + split_k - 1) / split_k;
   TileSched sched;
-  sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC));
+  sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC), reverse_m);
   if (kMC == 1 && dyn) {
     sched.dyn = 1, sched.role = (warp == 0) ? (leader ? 0 : 1) : 2;
     sched.clc_resp = smem_u32(clc_resp), sched.clc_full = clc_full, sched.clc_empty = clc_empty;
@@ -885,7 +896,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   if (dyn) clusters = units;  // one cluster per unit; the running ones cancel and absorb the rest
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, taux, ep, a->M, a->N, a->K,
-                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part, dyn);
+                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part, dyn, a->reverse_m ? 1 : 0);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
 }

@@ -29,6 +29,7 @@ from . import ops
 
 PRECISIONS = ("bf16", "fp32")
 _BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "0"))
+_ZIGZAG = os.environ.get("DITB200_ZIGZAG", "0") != "0"
 
 
 # --------------------------------------------------------------- parameter holders
@@ -272,29 +273,38 @@ class DiT(nn.Module):
         # (proj's k loop is too short to hide the f32 epilogue).  Chosen per build by measurement.
         branch = _BRANCH_MODE if bf16 else 0
         pend = None  # (branch output, gate) not yet folded into tok
+        # Traversal direction: every kernel of the chain walks the token rows the opposite way to its producer, so it
+        # starts on the rows that were written last and are still in the 126 MB L2 (results do not depend on it).
+        zig = _ZIGZAG and bf16
+        rv = [False]
+
+        def nxt():
+            rv[0] = zig and not rv[0]
+            return rv[0]
+
         for i, blk in enumerate(self.blocks):
             m = mod[:, i * 6 * D:(i + 1) * 6 * D]
             sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * D:(j + 1) * D] for j in range(6))
             if pend is None:
-                h = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=act)
+                h = ops.ln_modulate(tok, sh1, sc1, T, out_dtype=act, reverse=nxt())
             else:
-                _, h = ops.ln_modulate_resid(tok, pend[0], pend[1], sh1, sc1, T, out_dtype=act, x_out=tok)
+                _, h = ops.ln_modulate_resid(tok, pend[0], pend[1], sh1, sc1, T, out_dtype=act, x_out=tok, reverse=nxt())
                 pend = None
-            qkv = ops.gemm(h, w[4 * i], blk.attn.qkv.bias)
-            o = ops.attention(qkv, N, T, Hh, hd)
+            qkv = ops.gemm(h, w[4 * i], blk.attn.qkv.bias, reverse_m=nxt())
+            o = ops.attention(qkv, N, T, Hh, hd, reverse=nxt())
             if branch:
-                yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias)
-                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok)
+                yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, reverse_m=nxt())
+                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok, reverse=nxt())
             else:
                 ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
-                         rows_per_gate=T)
-                h = ops.ln_modulate(tok, sh2, sc2, T, out_dtype=act)
-            u = ops.gemm(h, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU)
+                         rows_per_gate=T, reverse_m=nxt())
+                h = ops.ln_modulate(tok, sh2, sc2, T, out_dtype=act, reverse=nxt())
+            u = ops.gemm(h, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU, reverse_m=nxt())
             if branch == 1:
-                pend = (ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias), g2)
+                pend = (ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, reverse_m=nxt()), g2)
             else:
                 ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g2,
-                         rows_per_gate=T)
+                         rows_per_gate=T, reverse_m=nxt())
         if pend is not None:  # last fc2 branch: plain update, the final layer normalises by itself
             ops.ln_modulate_resid(tok, pend[0], pend[1], None, None, T, x_out=tok, want_out=False)
         mf = mod[:, self.depth * 6 * D:]

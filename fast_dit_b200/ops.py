@@ -141,7 +141,8 @@ def label_embed(y, table, add=None):
 
 
 # ------------------------------------------------------- LayerNorm + modulate
-def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None, out=None):
+def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None, out=None,
+                reverse: bool = False):
     """x[B*T, D] f32; shift/scale: [B, D] views (unit inner stride, common row stride)."""
     lib = _lib_for(x)
     M, D = x.shape
@@ -151,12 +152,12 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
     if out is None:
         out = torch.empty((M, D), device=x.device, dtype=out_dtype)
     _call("ln_modulate", lib.ditb200_ln_modulate, _p(x), _p(shift), _p(scale), shift.stride(0), _p(out), _DT[out.dtype],
-                                    _p(stats), B, T, D, float(eps), _stream())
+                                    _p(stats), B, T, D, float(eps), int(reverse), _stream())
     return out
 
 
 def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None,
-                      x_out=None, want_out: bool = True):
+                      x_out=None, want_out: bool = True, reverse: bool = False):
     """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out)."""
     lib = _lib_for(x)
     M, D = x.shape
@@ -171,7 +172,7 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
     out = torch.empty((M, D), device=x.device, dtype=out_dtype) if want_out else None
     _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift if want_out else None),
           _p(scale if want_out else None), gate.stride(0), _p(x_out), _p(out), _DT[out_dtype], _p(stats), B, T, D,
-          float(eps), _stream())
+          float(eps), int(reverse), _stream())
     return x_out, out
 
 
@@ -179,7 +180,7 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
 def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
          rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0,
          aux_out=None, aux_in=None, accumulate: bool = False, split_k: int = 0, trans_a: bool = False,
-         trans_w: bool = False):
+         trans_w: bool = False, reverse_m: bool = False):
     """out = epilogue(op(a) @ op(w).T).  a[M,K] (or [K,M] with trans_a), w[N,K] (or [K,N] with trans_w), both
     bf16 (tcgen05) or both f32 (check mode, forward only)."""
     lib = _lib_for(a)
@@ -202,7 +203,7 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
                       _DT[out.dtype], engine, tile_n, cta_group,
                       _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
-                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC))
+                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC), int(reverse_m))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
           meta=2.0 * M * N * K,
           tag=None if _PROFILE is None else
@@ -242,13 +243,14 @@ def silu_cast(x, out_dtype=torch.bfloat16):
 
 
 # ------------------------------------------------------------------ attention
-def attention(qkv, B: int, T: int, H: int, hd: int, lse=None, out=None):
+def attention(qkv, B: int, T: int, H: int, hd: int, lse=None, out=None, reverse: bool = False):
     """qkv[B*T, 3*H*hd] -> out[B*T, H*hd], same dtype (bf16 or f32)."""
     lib = _lib_for(qkv)
     _chk_contig(qkv)
     if out is None:
         out = torch.empty((B * T, H * hd), device=qkv.device, dtype=qkv.dtype)
-    _call("attention_fwd", lib.ditb200_attention_fwd, _p(qkv), _p(out), _p(lse), _DT[qkv.dtype], B, T, H, hd, _stream(),
+    _call("attention_fwd", lib.ditb200_attention_fwd, _p(qkv), _p(out), _p(lse), _DT[qkv.dtype], B, T, H, hd,
+          int(reverse), _stream(),
           meta=4.0 * B * H * T * T * hd)
     return out
 

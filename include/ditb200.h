@@ -130,10 +130,11 @@ int ditb200_label_embed(const int64_t* y, const float* table, const float* add, 
  * (models_original.py:19-20,107,109,120-121).
  * x[B*T, D] f32; shift/scale point at [B, D] slices with row stride mod_stride
  * (floats); out[B*T, D] of out_dtype.  If stats != NULL, writes mean and rstd
- * per row to stats[2*row], stats[2*row+1] (saved for backward). */
+ * per row to stats[2*row], stats[2*row+1] (saved for backward).  reverse != 0: rows are visited last-first
+ * (L2 reuse between neighbouring kernels of a chain, see ditb200_gemm_args.reverse_m); same results. */
 int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, int mod_stride,
                         void* out, int out_dtype, float* stats, int B, int T, int D, float eps,
-                        void* stream);
+                        int reverse, void* stream);
 
 /* Gated residual update fused in front of ditb200_ln_modulate (the training forward keeps the branch output y
  * for backward, so the GEMM that produces it needs no residual traffic of its own):
@@ -143,7 +144,7 @@ int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, 
  * out bf16 or f32; stats as in ditb200_ln_modulate.  D must be 384, 768, 1024 or 1152. */
 int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
                               const float* scale, int mod_stride, float* x_out, void* out, int out_dtype,
-                              float* stats, int B, int T, int D, float eps, void* stream);
+                              float* stats, int B, int T, int D, float eps, int reverse, void* stream);
 
 /* Backward of ditb200_ln_modulate with respect to x, shift and scale.
  * dh[B*T, D] (dh_dtype) is the gradient of the modulated output; x, scale, stats as in the forward.
@@ -218,6 +219,9 @@ typedef struct ditb200_gemm_args {
                           clusters cancel and absorb the ones not yet launched, so SMs held by another kernel (the
                           overlapped NCCL all-reduce of a data-parallel backward, the role of torch DDP in
                           train_options/train_original.py:149) never own tiles.  Same results bit for bit. */
+  int reverse_m;       /* TCGEN05: visit the tile rows last-first.  Kernels of a chain alternate their direction so
+                          that each starts on the rows its producer wrote last (still in the 126 MB L2).  Same
+                          results bit for bit. */
 } ditb200_gemm_args;
 
 /* out = epilogue(a · wᵀ).  Replaces, per DiTBlock: timm Attention.qkv (EPI_BIAS),
@@ -242,9 +246,10 @@ int ditb200_silu_cast(const float* in, void* out, int out_dtype, size_t n, void*
  * + transpose/reshape (see performance/A100/train_original.out:36-37 for the layout).
  * qkv[B*T, 3*H*hd] token-major as the qkv Linear writes it (cols: Q heads | K heads |
  * V heads); out[B*T, H*hd] token-major (what proj consumes).  dtype of both =
- * dtype.  lse (optional, f32 [B,H,T]) receives log-sum-exp rows for backward. */
+ * dtype.  lse (optional, f32 [B,H,T]) receives log-sum-exp rows for backward.  reverse != 0: the (image, head)
+ * items are visited last-first (tcgen05 kernels; L2 reuse, see ditb200_gemm_args.reverse_m); same results. */
 int ditb200_attention_fwd(const void* qkv, void* out, float* lse, int dtype, int B, int T, int H,
-                          int hd, void* stream);
+                          int hd, int reverse, void* stream);
 
 /* Backward of ditb200_attention_fwd.  qkv/out/dout/dqkv in `dtype`; lse f32 [B,H,T] from the forward;
  * dsum f32 [B,H,T] is caller-owned scratch (row sums of dout*out).  dqkv[B*T, 3*H*hd] is written in

@@ -50,7 +50,7 @@ def test_argument_errors_without_gpu():
     from fast_dit_b200 import _lib
 
     lib = _lib.load()
-    rc = lib.ditb200_ln_modulate(None, None, None, 0, None, 0, None, 1, 1, 4, ctypes.c_float(1e-6), None)
+    rc = lib.ditb200_ln_modulate(None, None, None, 0, None, 0, None, 1, 1, 4, ctypes.c_float(1e-6), 0, None)
     assert rc == -1
     assert b"null pointer" in lib.ditb200_last_error()
     args = _lib.GemmArgs()

@@ -198,3 +198,38 @@ def test_branch_modes_match_fused_epilogue(monkeypatch, mode):
         alt = mc(x.cuda(), t.cuda(), y.cuda())
     assert rel_l2(base, ref) < 1e-2 and rel_l2(alt, ref) < 1e-2
     assert rel_l2(alt, base) < 5e-3
+
+
+def test_zigzag_traversal_is_bit_identical(monkeypatch):
+    """Alternating traversal direction of the kernels in the chain (reverse_m / reverse: L2 reuse between
+    neighbouring kernels) only changes the ORDER in which rows are visited: outputs must not change at all."""
+    from fast_dit_b200 import models, ops
+
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, K, N, T = 4096 + 256, 1152, 1152, 256
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    assert torch.equal(ops.gemm(a, w, bias), ops.gemm(a, w, bias, reverse_m=True))
+    for tile_n, cg in ((192, 2), (256, 2), (128, 1)):
+        assert torch.equal(ops.gemm(a, w, bias, tile_n=tile_n, cta_group=cg),
+                           ops.gemm(a, w, bias, tile_n=tile_n, cta_group=cg, reverse_m=True))
+    x = torch.randn(M, N, device="cuda", generator=g)
+    mod = torch.randn(M // T + 1, 3 * N, device="cuda", generator=g)
+    sh, sc, gt = mod[:, :N], mod[:, N:2 * N], mod[:, 2 * N:]
+    assert torch.equal(ops.ln_modulate(x, sh, sc, T), ops.ln_modulate(x, sh, sc, T, reverse=True))
+    y = ops.gemm(a, w, bias)
+    r0 = ops.ln_modulate_resid(x, y, gt, sh, sc, T)
+    r1 = ops.ln_modulate_resid(x, y, gt, sh, sc, T, reverse=True)
+    assert torch.equal(r0[0], r1[0]) and torch.equal(r0[1], r1[1])
+    B, H, hd = 20, 16, 72
+    qkv = torch.randn(B * T, 3 * H * hd, device="cuda", generator=g).bfloat16()
+    assert torch.equal(ops.attention(qkv, B, T, H, hd), ops.attention(qkv, B, T, H, hd, reverse=True))
+    m = build_product_model("DiT-S/2", input_size=32, num_classes=1000, precision="bf16").cuda()
+    xx, t, yy = _inputs(6, 32, 4)
+    with torch.no_grad():
+        monkeypatch.setattr(models, "_ZIGZAG", False)
+        base = m(xx.cuda(), t.cuda(), yy.cuda())
+        monkeypatch.setattr(models, "_ZIGZAG", True)
+        zig = m(xx.cuda(), t.cuda(), yy.cuda())
+    assert torch.equal(base, zig)
