@@ -48,7 +48,7 @@ NVCC_FLAGS = [
     "-Xptxas",
     "-v",
 ]
-# measurement variants (tools/ab.sh): e.g. DITB200_NVCC_EXTRA=-DDITB200_PDL builds the programmatic-dependent-launch
+# measurement variants (tools/ab.sh): e.g. DITB200_NVCC_EXTRA=-DDITB200_NO_PDL builds the library without programmatic dependent launch
 # variant of the hot kernels; part of the fingerprint, so switching it rebuilds
 NVCC_FLAGS += os.environ.get("DITB200_NVCC_EXTRA", "").split()
 

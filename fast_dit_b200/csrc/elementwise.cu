@@ -540,7 +540,7 @@ using namespace ditb200;
 // ------------------------------------------------------------------ C entry points
 extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const float* scale,
                                    int mod_stride, void* out, int out_dtype, float* stats, int B,
-                                   int T, int D, float eps, void* stream) {
+                                   int T, int D, float eps, int reverse, void* stream) {
   DITB_REQUIRE(x && shift && scale && out, DITB200_EINVAL, "ln_modulate: null pointer");
   DITB_REQUIRE(B > 0 && T > 0 && D > 0 && D % 4 == 0, DITB200_EINVAL,
                "ln_modulate: need B,T > 0 and D %% 4 == 0 (D=%d)", D);

@@ -28,7 +28,7 @@ from . import _lib as L
 from . import ops
 
 PRECISIONS = ("bf16", "fp32")
-_BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "0"))
+_BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "2"))
 _ZIGZAG = os.environ.get("DITB200_ZIGZAG", "0") != "0"
 
 
