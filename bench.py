@@ -106,32 +106,64 @@ def build_inputs_host(n, lat, seed):
 
 
 # ------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's own CPU path: the oracle port (torch fp32 on all host threads).  Each step is a
-    bounded sample of the workload: ONE CFG denoising step (model forward at batch 2*n_ref + the
-    diffusion update); images/s is extrapolated to the 250-step loop and says so."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def load_reference():
+    """The UNMODIFIED reference modules of the hot path (train_options/models_original.py + diffusion/) from
+    baseline/_ref/, where __graft_entry__.install_reference() placed them; timm (not installed in this image) is
+    provided by oracle/timm_standin.  Returns (models_original, diffusion package) or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not (os.path.isfile(os.path.join(ref, "models_original.py")) and os.path.isdir(os.path.join(ref, "diffusion"))):
+        return None
+    import importlib
+
+    saved_path, saved_mods = list(sys.path), {k: sys.modules.pop(k) for k in list(sys.modules) if k == "diffusion" or k.startswith("diffusion.")}
+    sys.path[:0] = [ref, os.path.join(ROOT, "oracle", "timm_standin")]
+    try:
+        mo = importlib.import_module("models_original")
+        rd = importlib.import_module("diffusion")
+        return mo, rd
+    except Exception as e:  # noqa: BLE001 -- fall back to the port, say why
+        print(f"[bench] reference import failed ({e!r}); using the oracle port", file=sys.stderr)
+        sys.modules.update(saved_mods)
+        return None
+    finally:
+        sys.path[:] = saved_path
+
+
+def reference_stepper(name, lat, spec, n_ref):
+    """One CFG denoising step of the workload on the host: (callable(step index), kind, steps_total).  With the
+    reference installed the step is the reference's own `diffusion.p_sample(model.forward_with_cfg, ...)`
+    (sample.py:51-64's call pattern, one iteration of gaussian_diffusion.py:498-511); otherwise the oracle port."""
     from oracle import dit_oracle as O
-    from oracle.diffusion_oracle import DiffusionOracle
     from fast_dit_b200.models import DiT_models
 
-    name, lat, _, spec = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    n_ref = args.ref_images
+    z, y = build_inputs_host(n_ref, lat, 0)
+    x = torch.cat([z, z], 0)
+    yy = torch.cat([y, torch.full((n_ref,), 1000)])
+    ref = load_reference()
+    if ref is not None:
+        MO, RD = ref
+        torch.manual_seed(0)
+        m = MO.DiT_models[name](input_size=lat, num_classes=1000)
+        O.rerandomise_zero_params(m.named_parameters())
+        m.eval()
+        d = RD.create_diffusion(spec)
+        torch.manual_seed(1)
+
+        def one_step(i):
+            t = torch.full((2 * n_ref,), i, dtype=torch.long)
+            with torch.no_grad():
+                return d.p_sample(m.forward_with_cfg, x, t, clip_denoised=False, model_kwargs=dict(y=yy, cfg_scale=CFG_SCALE))["sample"]
+
+        return one_step, "reference", d.num_timesteps
+    from oracle.diffusion_oracle import DiffusionOracle
+
     torch.manual_seed(0)
     m = DiT_models[name](input_size=lat, num_classes=1000)  # parameter container only (CPU); weights by protocol
     O.rerandomise_zero_params(m.named_parameters())
     sd = {k: v.detach() for k, v in m.state_dict().items()}
     cfg = O.config_for(name, input_size=lat)
     d = DiffusionOracle(spec)
-    z, y = build_inputs_host(n_ref, lat, 0)
-    x = torch.cat([z, z], 0)
-    yy = torch.cat([y, torch.full((n_ref,), 1000)])
     g = torch.Generator().manual_seed(1)
-    steps_total = d.num_timesteps
 
     def one_step(i):
         t = torch.full((2 * n_ref,), i, dtype=torch.long)
@@ -139,6 +171,32 @@ def run_reference(args):
             out = O.dit_forward_with_cfg(sd, cfg, x, d.map_t(t), yy, CFG_SCALE)
             return d.p_sample(out, x, t, torch.randn(x.shape, generator=g), clip_denoised=False)["sample"]
 
+    return one_step, "port", d.num_timesteps
+
+
+def run_reference(args):
+    """The reference's own CPU path (unmodified models_original.py + diffusion/ from baseline/_ref when installed,
+    else the oracle port), fp32 torch on all host threads, on the bench workload: each step is a bounded sample of it
+    — ONE CFG denoising step (model forward + diffusion update) at the workload's batch where the run then still
+    ends within a few minutes, else at the largest batch that does; images/s is extrapolated to the full loop and
+    says so."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, lat, n_full, spec = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_ref = args.ref_images
+    if n_ref <= 0:  # probe: seconds per image-forward at a small batch -> largest batch that fits ~200 s
+        probe, _, _ = reference_stepper(name, lat, spec, 2)
+        probe(0)
+        t0 = time.perf_counter()
+        probe(1)
+        per_img = (time.perf_counter() - t0) / 2
+        n_ref = n_full
+        while n_ref > 2 and per_img * n_ref * (args.steps + args.warmup) > 200.0:
+            n_ref //= 2
+    one_step, kind, steps_total = reference_stepper(name, lat, spec, n_ref)
     for w in range(args.warmup):
         one_step(steps_total - 1 - w)
     t0 = time.perf_counter()
@@ -146,16 +204,20 @@ def run_reference(args):
         one_step(steps_total - 1 - (k % steps_total))
     dt = (time.perf_counter() - t0) / args.steps
     value = n_ref / (steps_total * dt)
-    sample = (f"{args.steps} timed CFG denoising steps of {name} at {n_ref} kept images (batch {2 * n_ref}), fp32, "
-              f"{torch.get_num_threads()} threads; images/s = n / ({steps_total} steps x {dt:.3f} s/step), extrapolated")
+    what = "the unmodified reference (baseline/_ref: models_original.py + diffusion/, timm via oracle/timm_standin)" \
+        if kind == "reference" else "the oracle port of the reference"
+    sample = (f"{args.steps} timed CFG denoising steps of {name} at {n_ref} kept images (batch {2 * n_ref}; the workload "
+              f"has {n_full}) through {what}, fp32, {torch.get_num_threads()} threads; images/s = n / ({steps_total} "
+              f"steps x {dt:.3f} s/step), extrapolated")
     line = {
         "impl": "reference", "metric": f"{name} {lat * 8}px {steps_total}-step CFG-{CFG_SCALE} sampling throughput",
         "value": value,
         "unit": "img/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name} {lat}x{lat}x4 latent, {steps_total}-step DDPM, CFG {CFG_SCALE}",
-                   "step_is": "one CFG denoising step (bounded sample)"},
-        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": f"{name} {lat}x{lat}x4 latent, {steps_total}-step DDPM sampling, CFG {CFG_SCALE}, "
+                               f"{n_full} kept images/GPU (denoiser batch {2 * n_full}), random-init weights",
+                   "step_is": f"one CFG denoising step at {n_ref} kept images (bounded sample of the workload)"},
+        "cpu_baseline": {"value": value, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -163,33 +225,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------ our arm
-def cpu_baseline(name, lat, spec, budget_s=20.0):
-    """Oracle on the host cores, bounded to ~budget_s of CPU work."""
-    from oracle import dit_oracle as O
-    from oracle.diffusion_oracle import DiffusionOracle
-    from fast_dit_b200.models import DiT_models
-
+def cpu_baseline(name, lat, spec, budget_s=20.0, n_ref=8):
+    """The reference (or its oracle port) on the host cores, bounded to ~budget_s of CPU work."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_ref = 2
-    torch.manual_seed(0)
-    m = DiT_models[name](input_size=lat, num_classes=1000)
-    O.rerandomise_zero_params(m.named_parameters())
-    sd = {k: v.detach() for k, v in m.state_dict().items()}
-    cfg = O.config_for(name, input_size=lat)
-    d = DiffusionOracle(spec)
-    z, y = build_inputs_host(n_ref, lat, 0)
-    x = torch.cat([z, z], 0)
-    yy = torch.cat([y, torch.full((n_ref,), 1000)])
-    g = torch.Generator().manual_seed(1)
-    T = d.num_timesteps
-
-    def one_step(i):
-        t = torch.full((2 * n_ref,), i, dtype=torch.long)
-        with torch.no_grad():
-            out = O.dit_forward_with_cfg(sd, cfg, x, d.map_t(t), yy, CFG_SCALE)
-            d.p_sample(out, x, t, torch.randn(x.shape, generator=g), clip_denoised=False)
-
+    one_step, kind, T = reference_stepper(name, lat, spec, n_ref)
     one_step(T - 1)
     t0 = time.perf_counter()
     k = 0
@@ -199,9 +239,10 @@ def cpu_baseline(name, lat, spec, budget_s=20.0):
         if k >= 3 and (time.perf_counter() - t0 > budget_s or k >= 12):
             break
     dt = (time.perf_counter() - t0) / k
-    return {"value": n_ref / (T * dt), "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": f"{k} CFG denoising steps of {name} at {n_ref} kept images (batch {2 * n_ref}) after 1 warm-up, fp32 "
-                      f"torch on {torch.get_num_threads()} threads: {dt:.3f} s/step, extrapolated x{T} steps"}
+    src = "the unmodified reference in baseline/_ref" if kind == "reference" else "the oracle port"
+    return {"value": n_ref / (T * dt), "unit": "img/s", "cores": cores, "kind": kind,
+            "sample": f"{k} CFG denoising steps of {name} at {n_ref} kept images (batch {2 * n_ref}) after 1 warm-up through "
+                      f"{src}, fp32 torch on {torch.get_num_threads()} threads: {dt:.3f} s/step, extrapolated x{T} steps"}
 
 
 def run_ours(args):
@@ -471,7 +512,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS) + list(TRAIN_WORKLOADS))
     ap.add_argument("--images", type=int, default=0, help="kept images per GPU (default: the workload's)")
-    ap.add_argument("--ref-images", type=int, default=2, help="kept images per reference step")
+    ap.add_argument("--ref-images", type=int, default=0,
+                    help="kept images per reference step (0: the workload's, halved until the run fits ~200 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"],
                     help="training workloads, N > 1: wire format of the gradient all-reduce (f32 = the reference's DDP)")

@@ -60,6 +60,15 @@ class FusedAdamWEMA:
             ops.cast_bf16(self.flat, out=self.shadow)
         self._versions = self._snapshot()
 
+    @torch.no_grad()
+    def resync_from_parameters(self, reset_ema: bool = True):
+        """The parameters were overwritten from outside (data-parallel broadcast, manual edits through .data, which
+        do not bump tensor versions): rebuild the bf16 shadows and, like the reference's
+        `update_ema(ema, model, decay=0)` (train.py:179), restart the EMA from the new weights."""
+        self.refresh()
+        if reset_ema and self.ema is not None:
+            self.ema.copy_(self.flat)
+
     def shadows(self):
         if self._versions != self._snapshot():
             self.refresh()
@@ -107,16 +116,74 @@ class FusedAdamWEMA:
                 p.grad.zero_()
 
     # --------------------------------------------------------------------------------- checkpoints
+    def _named_views(self, arena):
+        """{parameter name: view of `arena` (one of the flat f32 arenas) for that parameter}."""
+        ids = {id(p): self.layout.view(arena, p) for p in self.params}
+        return {k: ids[id(v)] for k, v in self.model.named_parameters() if id(v) in ids}
+
     def ema_state_dict(self):
         """state_dict of the EMA model (what train.py:233 saves under "ema"; download.py:26-29 loads it)."""
+        if self.ema is None:
+            raise L.Ditb200Error("this optimizer was built with ema_decay=None: there is no EMA model")
         ids = {id(p): self.layout.view(self.ema, p) for p in self.params}
         return {k: ids.get(id(v), v).detach().clone() for k, v in self.model.state_dict(keep_vars=True).items()}
 
-    def state_dict(self):
-        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+    @torch.no_grad()
+    def load_ema_state_dict(self, sd):
+        """Restore the EMA weights from a model-style state_dict (the "ema" entry of a train.py checkpoint,
+        train.py:231-236).  Frozen entries (pos_embed) are ignored."""
+        if self.ema is None:
+            raise L.Ditb200Error("this optimizer was built with ema_decay=None: there is no EMA model")
+        views = self._named_views(self.ema)
+        missing = [k for k in views if k not in sd]
+        if missing:
+            raise KeyError(f"EMA state_dict lacks {missing[:3]}{'...' if len(missing) > 3 else ''}")
+        for k, v in views.items():
+            v.copy_(sd[k].to(v.device, torch.float32).reshape(v.shape))
 
+    def state_dict(self):
+        """Checkpoint of the optimizer in torch.optim.AdamW's format — {"state": {i: {"step", "exp_avg",
+        "exp_avg_sq"}}, "param_groups": [...]} with i = position in model.parameters(), the numbering torch's
+        AdamW(model.parameters()) uses (train.py:161, saved as "opt" at train.py:234; the frozen pos_embed takes a
+        number but has no state) — plus the EMA weights under "ema" (per-parameter, cloned).  Every tensor is a copy."""
+        m, v = self._named_views(self.exp_avg), self._named_views(self.exp_avg_sq)
+        names = [k for k, p in self.model.named_parameters()]
+        step = torch.tensor(float(self.step_count))
+        state = {i: {"step": step.clone(), "exp_avg": m[k].detach().clone(), "exp_avg_sq": v[k].detach().clone()}
+                 for i, k in enumerate(names) if k in m}
+        # every key this torch version's AdamW keeps in a param group (a loader fills absent ones with Adam's
+        # defaults, which would silently turn decoupled weight decay off)
+        group = dict(torch.optim.AdamW([torch.zeros(1)], lr=self.lr, betas=tuple(self.betas), eps=self.eps,
+                                       weight_decay=self.weight_decay).state_dict()["param_groups"][0])
+        group["params"] = list(range(len(names)))
+        out = {"state": state, "param_groups": [group], "param_names": names}
+        if self.ema is not None:
+            out["ema"] = {k: t.detach().clone() for k, t in self._named_views(self.ema).items()}
+        return out
+
+    @torch.no_grad()
     def load_state_dict(self, sd):
-        self.step_count = int(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        """Accepts this class's state_dict() and a plain torch.optim.AdamW state_dict over the same parameters (the
+        "opt" entry of a reference checkpoint).  A missing "ema" entry leaves the EMA untouched: restore it with
+        load_ema_state_dict(checkpoint["ema"])."""
+        names = [k for k, p in self.model.named_parameters()]
+        state = sd["state"]
+        m, v = self._named_views(self.exp_avg), self._named_views(self.exp_avg_sq)
+        if len(state) not in (0, len(m)) or any(int(i) >= len(names) or names[int(i)] not in m for i in state):
+            raise ValueError(f"optimizer state holds {len(state)} parameters, the model has {len(m)} trainable ones")
+        state = {int(i): st for i, st in state.items()}
+        steps = set()
+        for i, k in enumerate(names):
+            if i not in state:
+                continue
+            st = state[i]
+            m[k].copy_(st["exp_avg"].to(m[k].device, torch.float32).reshape(m[k].shape))
+            v[k].copy_(st["exp_avg_sq"].to(v[k].device, torch.float32).reshape(v[k].shape))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ; the fused step keeps one counter")
+        self.step_count = steps.pop() if steps else 0
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps, self.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+        if "ema" in sd and self.ema is not None:
+            self.load_ema_state_dict(sd["ema"])

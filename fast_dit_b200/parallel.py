@@ -132,7 +132,14 @@ class DataParallel(torch.nn.Module):
         if self.world > 1 and broadcast_parameters:
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):
-                    dist.broadcast(t.data, src=0, group=process_group)
+                    dist.broadcast(t.detach(), src=0, group=process_group)
+            # An optimizer built BEFORE this wrapper (bench.py's order) holds bf16 shadows and an EMA copy of the
+            # pre-broadcast weights; with per-rank seeds (train.py: seed = global_seed * world + rank before the
+            # model is built) those differ from rank 0's.  The reference re-syncs at train.py:179
+            # (update_ema(ema, model, decay=0) after DDP); same here.
+            flat = getattr(module, "_flat", None)
+            if flat is not None:
+                flat.resync_from_parameters()
         module._grad_sync = self._sync
 
     def _sync(self, key, arena):

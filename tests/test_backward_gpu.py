@@ -430,3 +430,73 @@ def test_fused_adamw_ema_matches_torch(dev):
         m.load_state_dict(ema_sd)
         ema_ref.eval()
         assert rel_l2(m(x, t, y), ema_ref(x, t, y)) < 1e-3
+
+
+def test_optimizer_checkpoint_round_trip_and_torch_adamw_interchange(dev):
+    """FusedAdamWEMA.state_dict() is torch.optim.AdamW's format (+ the EMA weights): (i) a saved and reloaded
+    optimizer continues exactly like the one that was never interrupted — including the EMA, which a resume must
+    not reset (train.py:231-236 saves {"model", "ema", "opt"}); (ii) torch.optim.AdamW over the same parameters loads
+    our checkpoint, and we load torch's own state_dict, after which both take identical steps."""
+    import copy
+
+    from fast_dit_b200.optim import FusedAdamWEMA
+    from util import build_product_model
+
+    def grads(model, seed):
+        g = _g(seed)
+        x = torch.randn(3, 4, 32, 32, device=dev, generator=g)
+        t = torch.randint(0, 1000, (3,), device=dev, generator=g)
+        y = torch.randint(0, 1000, (3,), device=dev, generator=g)
+        dout = torch.randn(3, 8, 32, 32, device=dev, generator=g)
+        torch.manual_seed(seed)
+        model(x, t, y).backward(dout)
+
+    m = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16").cuda().train()
+    opt = FusedAdamWEMA(m, lr=2e-3, weight_decay=0.01, ema_decay=0.9)
+    for s in (1, 2):
+        grads(m, s)
+        opt.step()
+        opt.zero_grad()
+    ck = {"model": copy.deepcopy(m.state_dict()), "ema": opt.ema_state_dict(), "opt": opt.state_dict()}
+    assert ck["opt"]["state"][1]["exp_avg"].data_ptr() != opt.exp_avg.data_ptr()  # copies, not live views
+    assert 0 not in ck["opt"]["state"], "pos_embed is parameter 0 of model.parameters() and frozen: no state"
+    grads(m, 3)
+    opt.step()
+    opt.zero_grad()
+    want_w = {k: v.clone() for k, v in m.state_dict().items()}
+    want_ema = opt.ema_state_dict()
+
+    # (i) resume in a fresh process' worth of objects
+    m2 = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16", seed=5).cuda().train()
+    m2.load_state_dict(ck["model"])
+    opt2 = FusedAdamWEMA(m2, lr=1.0, weight_decay=0.5, ema_decay=0.9)
+    opt2.load_state_dict(ck["opt"])
+    assert opt2.step_count == 2 and opt2.lr == 2e-3 and opt2.weight_decay == 0.01
+    for k, v in opt2.ema_state_dict().items():
+        assert torch.equal(v, ck["ema"][k]), k
+    grads(m2, 3)
+    opt2.step()
+    for k, v in m2.state_dict().items():
+        assert rel_l2(v, want_w[k]) < 1e-6, k
+    for k, v in opt2.ema_state_dict().items():
+        assert rel_l2(v, want_ema[k]) < 1e-6, k
+
+    # (ii) interchange with torch.optim.AdamW
+    ref = copy.deepcopy(m2)
+    ref.load_state_dict(ck["model"])
+    topt = torch.optim.AdamW(ref.parameters(), lr=1.0)
+    topt.load_state_dict({k: v for k, v in ck["opt"].items() if k in ("state", "param_groups")})
+    m3 = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16", seed=6).cuda().train()
+    m3.load_state_dict(ck["model"])
+    opt3 = FusedAdamWEMA(m3, ema_decay=None)
+    opt3.load_state_dict(topt.state_dict())  # torch's own dict: no "ema", no "param_names"
+    grads(m3, 3)
+    for p, q in zip(m3.parameters(), ref.parameters()):
+        q.grad = None if p.grad is None else p.grad.clone()
+    opt3.step()
+    topt.step()
+    for (k, p), q in zip(m3.named_parameters(), ref.parameters()):
+        assert rel_l2(p, q) < 1e-6, k
+        assert rel_l2(p, want_w[k]) < 1e-6, k
+    with pytest.raises(Exception):
+        opt3.ema_state_dict()
