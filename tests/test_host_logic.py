@@ -182,8 +182,9 @@ def test_attention_dispatch(T, hd, backward, expect):
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) runs without a GPU and prints ONE JSON line with
-    the keys the driver reads; same metric / unit / workload naming as the GPU arm."""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref where it is installed, else the oracle
+    port, on the host cores) runs without a GPU and prints ONE JSON line with the keys the driver reads; same metric /
+    unit / workload naming as the GPU arm."""
     import json
     import os
     import subprocess
@@ -199,4 +200,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "img/s" and d["higher_is_better"] is True
     assert "250-step" in d["metric"] and d["config"]["workload"].startswith("DiT-XL/2")
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
+    installed = os.path.isfile(os.path.join(root, "baseline", "_ref", "models_original.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if installed else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["gpu_launches"] == 0
+    assert d["config"]["workload"].endswith("random-init weights") and "32 kept images/GPU" in d["config"]["workload"]
