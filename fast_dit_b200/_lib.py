@@ -75,7 +75,7 @@ SIGNATURES = {
     "ditb200_debug_attention_path": (_i, [_i] * 3),
     "ditb200_sm_count": (_i, []),
     "ditb200_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "ditb200_timestep_embedding": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "ditb200_timestep_embedding": (_i, [_vp, _i, _vp, _i, _i, _f, _vp]),
     "ditb200_small_linear": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_label_embed": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp]),

@@ -44,10 +44,14 @@ extern "C" int ditb200_sm_count(void) { return g_sms; }
 extern "C" int ditb200_init(int device) {
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (g_init && g_device == device) return 0;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return check_cuda(e, "cudaSetDevice");
+  // One device per process (one process per GPU is how the path is deployed: sample_ddp.py:54-58): the function
+  // attributes, SM count and cluster occupancy the launchers cache are per device.
+  if (g_init) {
+    set_error("libditb200 is bound to device %d in this process; refusing device %d (one process per GPU)", g_device, device);
+    return DITB200_EINVAL;
+  }
   cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, device);
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);  // does not change the caller's current device
   if (e != cudaSuccess) return check_cuda(e, "cudaGetDeviceProperties");
   if (prop.major != 10) {
     set_error("libditb200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major,

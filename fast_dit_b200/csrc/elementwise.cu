@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(320, 1) patch_embed_k16_kernel(
 }
 
 // ============================================================= timestep sinusoid
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out,
+__global__ void timestep_embedding_kernel(const void* __restrict__ t, int t_is_float, float* __restrict__ out,
                                           int B, int dim, float neg_log_period) {
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,7 +354,8 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
     const int k = (j < half) ? j : j - half;
     // freqs = exp(-log(P) * arange(half) / half), every op rounded to f32 as torch does
     const float f = expf(__fdiv_rn(__fmul_rn(neg_log_period, (float)k), (float)half));
-    const float a = __fmul_rn((float)t[b], f);
+    const float tv = t_is_float ? reinterpret_cast<const float*>(t)[b] : (float)reinterpret_cast<const int64_t*>(t)[b];
+    const float a = __fmul_rn(tv, f);
     r = (j < half) ? cosf(a) : sinf(a);
   }
   out[idx] = r;
@@ -650,15 +651,14 @@ extern "C" int ditb200_patch_embed(const float* x, const float* w, const float* 
   return 0;
 }
 
-extern "C" int ditb200_timestep_embedding(const int64_t* t, float* out, int B, int dim,
+extern "C" int ditb200_timestep_embedding(const void* t, int t_is_float, float* out, int B, int dim,
                                           float max_period, void* stream) {
   DITB_REQUIRE(t && out && B > 0 && dim > 0 && max_period > 0.f, DITB200_EINVAL,
                "timestep_embedding: bad argument");
   const int n = B * dim;
   // -math.log(max_period) is a Python double that torch rounds to f32 when it meets the f32 arange
   const float neg_log = (float)(-log((double)max_period));
-  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, out, B, dim,
-                                                                                neg_log);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, t_is_float, out, B, dim, neg_log);
   DITB_LAUNCH_CHECK("timestep_embedding");
   return 0;
 }

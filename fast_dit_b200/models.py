@@ -29,7 +29,7 @@ from . import ops
 
 PRECISIONS = ("bf16", "fp32")
 _BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "2"))
-_ZIGZAG = os.environ.get("DITB200_ZIGZAG", "0") != "0"
+_ZIGZAG = os.environ.get("DITB200_ZIGZAG", "1") != "0"
 
 
 # --------------------------------------------------------------- parameter holders
@@ -235,6 +235,19 @@ class DiT(nn.Module):
             return dit_forward_autograd(self, x, t, y)
         return self._forward_inference(x, t, y)
 
+    def _check_labels(self, y):
+        """nn.Embedding raises on an out-of-range index (MO:93); the gather kernel clamps instead.  The one
+        configuration where a caller can plausibly pass one is class_dropout_prob == 0: the table then has NO null
+        row, and forward_with_cfg's y = num_classes would silently read class num_classes - 1.  Checked on the host
+        there (one device->host read; never inside a CUDA-graph capture)."""
+        ye = self.y_embedder
+        if ye.dropout_prob > 0 or torch.cuda.is_current_stream_capturing():
+            return
+        rows = ye.embedding_table.weight.shape[0]
+        if y.numel() and (int(y.max()) >= rows or int(y.min()) < 0):
+            raise IndexError(f"label out of range for an embedding table of {rows} rows (class_dropout_prob == 0: "
+                             "there is no null-class row for classifier-free guidance)")
+
     def conditioning(self, t, y, force_drop_ids=None):
         """c = t_embedder(t) + y_embedder(y) (MO:241-243), f32 [N, D]."""
         te = self.t_embedder
@@ -243,6 +256,7 @@ class DiT(nn.Module):
         ye = self.y_embedder
         if (self.training and ye.dropout_prob > 0) or force_drop_ids is not None:
             y = ye.token_drop(y, force_drop_ids)
+        self._check_labels(y)
         y_emb = ops.label_embed(y, ye.embedding_table.weight)
         return ops.small_linear(h, te.mlp[2].weight, te.mlp[2].bias, add=y_emb)
 
@@ -271,7 +285,7 @@ class DiT(nn.Module):
         # produces the branch (f32 stream read + written there).  1 / 2: the GEMM stores the bf16 branch by TMA and
         # the update rides in front of the next LayerNorm (ln_modulate_resid), for proj + fc2 / for proj only
         # (proj's k loop is too short to hide the f32 epilogue).  Chosen per build by measurement.
-        branch = _BRANCH_MODE if bf16 else 0
+        branch = _BRANCH_MODE if (bf16 and D in (384, 768, 1024, 1152)) else 0  # widths ln_modulate_resid serves
         pend = None  # (branch output, gate) not yet folded into tok
         # Traversal direction: every kernel of the chain walks the token rows the opposite way to its producer, so it
         # starts on the rows that were written last and are still in the 126 MB L2 (results do not depend on it).

@@ -25,7 +25,12 @@ def _stream() -> int:
 def _lib_for(t: torch.Tensor):
     if not t.is_cuda:
         raise L.Ditb200Error("libditb200 ops need CUDA tensors (there is no CPU path)")
-    return L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        # kernels are launched on torch's CURRENT stream, which belongs to the current device
+        raise L.Ditb200Error(f"tensor lives on cuda:{idx} but the current device is cuda:{torch.cuda.current_device()}; "
+                             "call torch.cuda.set_device() first (one process per GPU)")
+    return L.ensure_init(idx)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -106,12 +111,16 @@ def patch_embed(x, w, bias, pos, p: int, round_bf16: bool = False):
 
 
 def timestep_embedding(t, dim: int, max_period: float = 10000.0):
+    """t[B] -> [B, dim] sinusoidal features.  Integer timesteps travel as int64; floating ones (the reference's
+    embedder accepts fractional t: models_original.py:40-59 does t[:, None].float()) as f32."""
     lib = _lib_for(t)
-    if t.dtype != torch.int64:
-        t = t.to(torch.int64)
-    t = t.contiguous()
+    if t.is_floating_point():
+        t, is_float = t.to(torch.float32).contiguous(), 1
+    else:
+        t, is_float = t.to(torch.int64).contiguous(), 0
     out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.float32)
-    _call("timestep_embedding", lib.ditb200_timestep_embedding, _p(t), _p(out), t.shape[0], dim, float(max_period), _stream())
+    _call("timestep_embedding", lib.ditb200_timestep_embedding, _p(t), is_float, _p(out), t.shape[0], dim,
+          float(max_period), _stream())
     return out
 
 

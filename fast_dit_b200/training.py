@@ -186,6 +186,7 @@ class _DiTFunction(torch.autograd.Function):
         pre1 = ops.small_linear(t_freq, te.mlp[0].weight, te.mlp[0].bias)
         h1 = ops.silu_cast(pre1, torch.float32)
         y_idx = ye.token_drop(y) if (model.training and ye.dropout_prob > 0) else y
+        model._check_labels(y_idx)
         y_emb = ops.label_embed(y_idx, ye.embedding_table.weight)
         c = ops.small_linear(h1, te.mlp[2].weight, te.mlp[2].bias, add=y_emb)
         sc = ops.silu_cast(c, torch.bfloat16)

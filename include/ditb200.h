@@ -101,8 +101,9 @@ int ditb200_patch_embed(const float* x, const float* w, const float* bias, const
 
 /* Sinusoidal timestep features, cos half first.
  * Replaces TimestepEmbedder.timestep_embedding (models_original.py:40-59).
- * t[B] int64 → out[B, dim] f32. */
-int ditb200_timestep_embedding(const int64_t* t, float* out, int B, int dim, float max_period,
+ * t[B] int64 (t_is_float == 0) or f32 (t_is_float != 0: the reference embeds fractional timesteps too, it
+ * computes t[:, None].float() * freqs) → out[B, dim] f32. */
+int ditb200_timestep_embedding(const void* t, int t_is_float, float* out, int B, int dim, float max_period,
                                void* stream);
 
 /* Small-M linear: out[m, n] = act_out( sum_k act_in(a[m,k]) * w[n,k] + bias[n] ) (+ add[m,n]).
