@@ -6,7 +6,7 @@ tag=$1; lib=$2; shift 2
 envs=()
 while [ "$1" != "--" ] && [ $# -gt 0 ]; do envs+=("$1"); shift; done
 shift
-cp "$lib" fast_dit_b200/lib/libditb200.so
+[ "$lib" -ef fast_dit_b200/lib/libditb200.so ] || cp "$lib" fast_dit_b200/lib/libditb200.so
 env "${envs[@]}" timeout 600 python bench.py --no-cpu-baseline "$@" > gpurun_out/$tag.json 2> gpurun_out/$tag.err
 python - "$tag" <<'P'
 import json, sys
