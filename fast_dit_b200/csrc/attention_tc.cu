@@ -339,331 +339,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
-// ============================================================ T <= 256, two threads per query row (round 2)
-// Same data flow as attn_fwd_tc_kernel above (S in TMEM, P written back as the TMEM A operand of P V, K/V ring of
-// two items), but every query row is shared by TWO softmax threads, each owning half of the row's keys: 16 softmax
-// warps instead of 8.  The kernel above was latency-bound — one thread per row makes every item a serial chain
-// (scores -> max pass -> exp pass -> P V -> O read -> store) with 2 softmax warps per scheduler, MUFU 43 % busy,
-// issue slots 30 % busy (profiles/r02_attention_tc_before.md).  Halving every link of the chain and doubling the
-// warps each scheduler can interleave is what the profile asked for.
-//   warp w < 16:  query tile t = w / 8, TMEM lane quarter q = w % 4 (the hardware's rule: a warp may touch lanes
-//                 32 (w % 4) ..), key half hf = (w / 4) % 2
-//   warp 16 TMA producer, warp 17 MMA issuer + TMEM allocation
-// TMEM, per query tile (256 columns):  S  [0, T)
-//   P keys [0, T/2)   -> packed bf16 at [0, T/4)          written by the hf = 0 thread over S columns it has read
-//   P keys [T/2, T)   -> packed bf16 at [T - T/4, T)      written by the hf = 1 thread, which walks its chunks
-//                                                          LAST-first so that P only ever lands on columns already
-//                                                          consumed by the SAME thread (no cross-thread hazard)
-//   O (80 columns)    -> [64, 144) for T = 256, [128, 208) for T = 128: clear of both P ranges
-// The two threads of a row exchange their partial maxima and sums through shared memory, synchronised by a
-// 64-thread named barrier per (tile, quarter) pair of warps.
-constexpr int kAt2Threads = 576;  // 16 softmax warps + producer + MMA
-struct Attn2Smem {
-  static constexpr int kQ0 = AttnSmem::kQ0, kQ1 = AttnSmem::kQ1, kK0 = AttnSmem::kK0, kK1 = AttnSmem::kK1;
-  static constexpr int kV0 = AttnSmem::kV0, kV1 = AttnSmem::kV1, kKV = AttnSmem::kKV;
-  static constexpr int oQ0 = 0, oQ1 = oQ0 + 2 * kQ0, oKV = oQ1 + 2 * kQ1;
-  static constexpr int kStgPitch = 32;                 // bytes per staged row: 16 output columns (two XOR-swizzled 16-byte slots)
-  static constexpr int kStg = 32 * kStgPitch;          // per softmax warp
-  static constexpr int oStg = oKV + 2 * kKV;
-  static constexpr int oXch = oStg + 16 * kStg;        // float [2 tiles][2 halves][128 rows] x {max, sum}
-  static constexpr int oBars = oXch + 2 * 2 * 2 * 128 * 4;
-  static constexpr int kBytes = oBars + 256 + 1024;
-};
-static_assert(Attn2Smem::kBytes <= 232448, "attention (2 threads / row): shared memory budget");
-
-__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
-__global__ void __launch_bounds__(kAt2Threads, 1)
-attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_k0,
-                    const __grid_constant__ CUtensorMap map_v0, const __grid_constant__ CUtensorMap map_q1,
-                    const __grid_constant__ CUtensorMap map_kv1, __nv_bfloat16* __restrict__ out,
-                    float* __restrict__ lse, const int B, const int T, const int H, const int hd,
-                    const float scale_log2e, const int reverse) {
-  using SM = Attn2Smem;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::oBars);
-  uint64_t* q_full = bars;          // [2]  TMA -> MMA      (per query tile)
-  uint64_t* q_empty = bars + 2;     // [2]  MMA -> TMA
-  uint64_t* kv_full = bars + 4;     // [2]  TMA -> MMA      (ring stage)
-  uint64_t* kv_empty = bars + 6;    // [2]  MMA -> TMA
-  uint64_t* s_full = bars + 8;      // [2]  MMA -> softmax  (S tile in TMEM)
-  uint64_t* p_full = bars + 10;     // [2]  softmax -> MMA  (P written, 256 arrivals)
-  uint64_t* o_full = bars + 12;     // [2]  MMA -> softmax  (O tile in TMEM)
-  uint64_t* s_free = bars + 14;     // [2]  softmax -> MMA  (region drained, 256 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
-  float* xch = reinterpret_cast<float*>(smem + SM::oXch);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nqt = T / kAtQ;          // query tiles per head: 1 or 2
-  const bool has_c1 = hd > 64;       // second channel chunk (64..79)
-  const int D = H * hd;
-  const int n_items = B * H;
-  const int p_hi = T - T / 4;                    // packed P of the upper key half
-  const int o_col = (T == 256) ? 64 : 128;       // O accumulator inside the region
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&map_q0), tma_prefetch_desc(&map_k0), tma_prefetch_desc(&map_v0);
-    tma_prefetch_desc(&map_q1), tma_prefetch_desc(&map_kv1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1), mbar_init(&q_empty[i], 1), mbar_init(&kv_full[i], 1), mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1), mbar_init(&p_full[i], 256), mbar_init(&o_full[i], 1), mbar_init(&s_free[i], 256);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 17) tmem_alloc<1>(tmem_ptr, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  DITB_PDL_TRIGGER();
-  DITB_PDL_WAIT();
-
-  if (warp == 16) {
-    // ================================================================== TMA producer
-    const uint32_t q_bytes = (uint32_t)(SM::kQ0 + (has_c1 ? SM::kQ1 : 0));
-    const uint32_t kv_bytes = (uint32_t)(2 * T * 128 + (has_c1 ? 2 * T * 32 : 0));
-    int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int wi = reverse ? n_items - 1 - w : w;
-      const int b = wi / H, h = wi - b * H;
-      const int stage = it & 1;
-      const uint32_t kvpar = (it >> 1) & 1, par = it & 1;
-      const int tok0 = b * T;
-      uint8_t* kv = smem + SM::oKV + stage * SM::kKV;
-      mbar_wait(&kv_empty[stage], kvpar ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&kv_full[stage], kv_bytes);
-        tma_load_3d(&map_k0, &kv_full[stage], kv, 0, H + h, tok0);
-        if (has_c1) tma_load_3d(&map_kv1, &kv_full[stage], kv + SM::kK0, 64, H + h, tok0);
-      }
-      __syncwarp();
-      for (int t = 0; t < nqt; ++t) {
-        mbar_wait(&q_empty[t], par ^ 1u);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&q_full[t], q_bytes);
-          tma_load_3d(&map_q0, &q_full[t], smem + SM::oQ0 + t * SM::kQ0, 0, h, tok0 + t * kAtQ);
-          if (has_c1) tma_load_3d(&map_q1, &q_full[t], smem + SM::oQ1 + t * SM::kQ1, 64, h, tok0 + t * kAtQ);
-        }
-        __syncwarp();
-      }
-      if (elect_one()) {
-        uint8_t* v0 = kv + SM::kK0 + SM::kK1;
-        for (int kb = 0; kb < T / 64; ++kb)  // V channels 0..63: {64 channels x 64 keys} boxes, 8 KB each
-          tma_load_3d(&map_v0, &kv_full[stage], v0 + kb * 8192, 0, 2 * H + h, tok0 + kb * 64);
-        if (has_c1) tma_load_3d(&map_kv1, &kv_full[stage], v0 + SM::kV0, 64, 2 * H + h, tok0);
-      }
-      __syncwarp();
-    }
-  } else if (warp == 17) {
-    // ==================================================================== MMA issuer
-    const uint32_t idesc_s = umma_idesc_bf16(kAtQ, (uint32_t)T);                 // S: 128 x T, both K-major
-    const uint32_t idesc_o64 = umma_idesc_bf16(kAtQ, 64) | (1u << 16);           // O[:, 0:64]: B = V, MN-major
-    const uint32_t idesc_o16 = umma_idesc_bf16(kAtQ, 16) | (1u << 16);           // O[:, 64:80]
-    auto issue_s = [&](int t, int stage) {
-      const uint32_t kv = smem_u32(smem + SM::oKV + stage * SM::kKV);
-      const uint32_t k0 = kv, k1 = kv + SM::kK0;
-      const uint32_t d = tmem_base + (uint32_t)(t * kAtRegion);
-      const uint32_t q0 = smem_u32(smem + SM::oQ0 + t * SM::kQ0);
-      const uint32_t q1 = smem_u32(smem + SM::oQ1 + t * SM::kQ1);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
-      if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
-      umma_commit<1>(&s_full[t]);
-      umma_commit<1>(&q_empty[t]);
-    };
-    auto issue_o = [&](int t, int stage, bool last) {
-      const uint32_t kv = smem_u32(smem + SM::oKV + stage * SM::kKV);
-      const uint32_t v0 = kv + SM::kK0 + SM::kK1, v1 = v0 + SM::kV0;
-      const uint32_t region = tmem_base + (uint32_t)(t * kAtRegion);
-      const uint32_t d = region + (uint32_t)o_col;
-      const int half_steps = T / 32;  // 16-key steps per key half
-      for (int ks = 0; ks < T / 16; ++ks) {  // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V
-        const uint32_t p = region + (uint32_t)(ks < half_steps ? 8 * ks : p_hi + 8 * (ks - half_steps));
-        umma_bf16_ts(d, p, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, ks > 0);
-        if (has_c1) umma_bf16_ts(d + 64, p, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, ks > 0);
-      }
-      umma_commit<1>(&o_full[t]);
-      if (last) umma_commit<1>(&kv_empty[stage]);
-    };
-    if ((int)blockIdx.x < n_items) {  // prologue: the score tiles of this CTA's first item
-      mbar_wait(&kv_full[0], 0u);
-      for (int t = 0; t < nqt; ++t) {
-        mbar_wait(&q_full[t], 0u);
-        tcgen05_fence_after();
-        if (elect_one()) issue_s(t, 0);
-        __syncwarp();
-      }
-    }
-    int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int stage = it & 1;
-      const uint32_t par = it & 1;
-      const bool has_next = w + (int)gridDim.x < n_items;
-      const int nstage = (it + 1) & 1;
-      const uint32_t nkvpar = ((it + 1) >> 1) & 1, npar = (it + 1) & 1;
-      for (int t = 0; t < nqt; ++t) {
-        mbar_wait(&p_full[t], par);
-        tcgen05_fence_after();
-        if (elect_one()) issue_o(t, stage, t == nqt - 1);
-        __syncwarp();
-        if (has_next) {
-          if (t == 0) mbar_wait(&kv_full[nstage], nkvpar);
-          mbar_wait(&q_full[t], npar);
-          mbar_wait(&s_free[t], par);  // both threads of every row have pulled O_t(i) out of the region
-          tcgen05_fence_after();
-          if (elect_one()) issue_s(t, nstage);
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    // ======================================== softmax + output, two threads per query row (key halves)
-    const int t = warp >> 3, quarter = warp & 3, hf = (warp >> 2) & 1;
-    if (t < nqt) {
-      const int row = quarter * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kAtRegion);
-      const int nch = T / 64;                                        // 32-key chunks per thread: 4 or 2
-      const uint32_t s_base = trow + (uint32_t)(hf * (T / 2));         // this thread's S columns
-      const uint32_t p_base = trow + (uint32_t)(hf ? p_hi : 0);        // where its packed P goes
-      const int bar_id = 1 + t * 4 + quarter;                          // named barrier of this row-pair of warps
-      float* my_x = xch + ((t * 2 + hf) * 128 + row) * 2;              // {max, sum} this thread publishes
-      const float* ot_x = xch + ((t * 2 + (hf ^ 1)) * 128 + row) * 2;  // the partner's
-      // chunk visited j-th: ascending for the lower half, descending for the upper (see the TMEM map above)
-      auto cidx = [&](int j) { return hf ? nch - 1 - j : j; };
-      const uint32_t stg = smem_u32(smem + SM::oStg) + (uint32_t)(warp * SM::kStg);
-      // O columns of this thread: [0, 40) / [40, 80) with a second channel chunk, else [0, 32) / [32, 64)
-      const int o_w = has_c1 ? 40 : 32, o_c0 = hf * o_w;
-      int it = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        const int wi = reverse ? n_items - 1 - w : w;
-        const int b = wi / H, h = wi - b * H;
-        const uint32_t par = it & 1;
-        mbar_wait(&s_full[t], par);
-        tcgen05_fence_after();
-        // ---- pass 1: maximum of this thread's half of the raw score row
-        uint32_t va[32], vb[32];
-        float mx = -INFINITY;
-        tmem_ld_32x32(s_base + 32 * cidx(0), va);
-        for (int j = 0; j < nch; j += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32(s_base + 32 * cidx(j + 1), vb);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(va[i + 1])));
-          tmem_ld_wait();
-          tmem_ld_32x32(s_base + 32 * cidx(j + 2 < nch ? j + 2 : 0), va);  // last round: first chunk again, for pass 2
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[i]), __uint_as_float(vb[i + 1])));
-        }
-        my_x[0] = mx;
-        pair_barrier(bar_id);
-        mx = fmaxf(mx, ot_x[0]);
-        // ---- pass 2: p = exp2((s - max) * scale * log2 e), partial row sum, P -> TMEM as packed bf16
-        const float msc = mx * scale_log2e;
-        float2 sum2 = make_float2(0.f, 0.f);
-        const float2 sl2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-msc, -msc);
-        uint32_t pk[16];
-        for (int j = 0; j < nch; j += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32(s_base + 32 * cidx(j + 1), vb);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 e = __ffma2_rn(f2(va[2 * i], va[2 * i + 1]), sl2, nm2);
-            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-            sum2 = __fadd2_rn(sum2, pp);
-            pk[i] = pack_bf16x2(pp.x, pp.y);
-          }
-          tmem_st_32x16(p_base + 16 * cidx(j), pk);
-          tmem_ld_wait();
-          if (j + 2 < nch) tmem_ld_32x32(s_base + 32 * cidx(j + 2), va);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 e = __ffma2_rn(f2(vb[2 * i], vb[2 * i + 1]), sl2, nm2);
-            const float2 pp = make_float2(ex2_approx(e.x), ex2_approx(e.y));
-            sum2 = __fadd2_rn(sum2, pp);
-            pk[i] = pack_bf16x2(pp.x, pp.y);
-          }
-          tmem_st_32x16(p_base + 16 * cidx(j + 1), pk);
-        }
-        float sum = sum2.x + sum2.y;
-        my_x[1] = sum;
-        tmem_st_wait();
-        tcgen05_fence_before();
-        mbar_arrive(&p_full[t]);
-        pair_barrier(bar_id);  // the partner's partial sum is visible; also orders this item's exchange against the next
-        sum += ot_x[1];
-        // ---- output: this thread's O columns / sum -> bf16, transposed through the warp's staging buffer
-        mbar_wait(&o_full[t], par);
-        tcgen05_fence_after();
-        uint32_t ov[40];  // this thread's O slice, thread-local column k = ov[k]
-        const uint32_t ocol = trow + (uint32_t)(o_col + o_c0);
-        if (has_c1) {
-          if (hf == 0) {
-            tmem_ld_32x32(ocol, reinterpret_cast<uint32_t(&)[32]>(ov[0]));
-            tmem_ld_32x8(ocol + 32, reinterpret_cast<uint32_t(&)[8]>(ov[32]));
-          } else {
-            tmem_ld_32x8(ocol, reinterpret_cast<uint32_t(&)[8]>(ov[0]));
-            tmem_ld_32x32(ocol + 8, reinterpret_cast<uint32_t(&)[32]>(ov[8]));
-          }
-        } else {
-          tmem_ld_32x32(ocol, reinterpret_cast<uint32_t(&)[32]>(ov[0]));
-        }
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(&s_free[t]);  // the accumulators are in registers: the region may take the next score tile
-        const float inv = 1.0f / sum;
-        __nv_bfloat16* obase = out + ((size_t)b * T + t * kAtQ + quarter * 32) * D + h * hd;
-        // flushes of 16 columns: every lane stages its row as two 16-byte slots (XOR-swizzled by row group: conflict-free
-        // both ways), then the warp stores 32-byte row segments, 16 rows per instruction
-        const uint32_t my = stg + (uint32_t)lane * SM::kStgPitch;
-        const int sw = (lane >> 2) & 1;
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-          const int k0 = 16 * f;
-          if (k0 < o_w) {  // warp-uniform
-            const int ng = (o_w - k0) >= 16 ? 2 : 1;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (g < ng) {
-                const int k = k0 + 8 * g;
-                sts128(my + (uint32_t)((g ^ sw) << 4),
-                       pack_bf16x2(__uint_as_float(ov[k]) * inv, __uint_as_float(ov[k + 1]) * inv),
-                       pack_bf16x2(__uint_as_float(ov[k + 2]) * inv, __uint_as_float(ov[k + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(ov[k + 4]) * inv, __uint_as_float(ov[k + 5]) * inv),
-                       pack_bf16x2(__uint_as_float(ov[k + 6]) * inv, __uint_as_float(ov[k + 7]) * inv));
-              }
-            }
-            __syncwarp();
-            const int g = lane & 1, col = o_c0 + k0 + 8 * g;
-            if (g < ng && col < hd) {
-#pragma unroll
-              for (int ps = 0; ps < 2; ++ps) {
-                const int r = ps * 16 + (lane >> 1);
-                const uint4 q4 = lds128_u(stg + (uint32_t)(r * SM::kStgPitch + ((g ^ ((r >> 2) & 1)) << 4)));
-                *reinterpret_cast<uint4*>(obase + (size_t)r * D + col) = q4;
-              }
-            }
-            __syncwarp();
-          }
-        }
-        if (lse != nullptr && hf == 0)
-          lse[((size_t)b * H + h) * T + t * kAtQ + row] = (msc + log2f(sum)) * 0.6931471805599453f;
-      }
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 17) tmem_dealloc<1>(tmem_base, 512);
-}
-
 // ============================================================================ long sequences (T > 256)
 // KV-blocked variant for T = 512, 768, 1024, ... (the 512 px configuration: 1024 tokens).  A work item is one
 // (image, head, PAIR of 128-query tiles); K and V stream through a 4-stage ring in blocks of 128 keys, each block
@@ -1346,19 +1021,6 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
   }
   int grid = num_sms();
   if (grid > B * H) grid = B * H;
-  static const bool one_per_row = getenv("DITB200_ATTN_1T") != nullptr;  // measurement switch: the round-1 kernel
-  if (!one_per_row) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Smem::kBytes);
-      if (e != cudaSuccess) return check_cuda(e, "attention_fwd(tcgen05, 2 threads/row) smem attribute");
-      attr2_set = true;
-    }
-    DITB_KLAUNCH(attn_fwd_tc2_kernel, grid, kAt2Threads, Attn2Smem::kBytes, st, mq0, mk0, mv0, mq1, mkv1,
-                 reinterpret_cast<__nv_bfloat16*>(out), lse, B, T, H, hd, scale_log2e, reverse ? 1 : 0);
-    DITB_LAUNCH_CHECK("attention_fwd(tcgen05, 2 threads/row)");
-    return 0;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::kBytes);
