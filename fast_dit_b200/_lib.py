@@ -84,7 +84,7 @@ SIGNATURES = {
     "ditb200_gate_resid_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "ditb200_colsum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "ditb200_label_embed_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    "ditb200_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ditb200_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_unpatchify_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ditb200_silu_bwd": (_i, [_vp, _vp, _vp, _i, _sz, _vp]),
     "ditb200_gemm": (_i, [C.POINTER(GemmArgs), _vp]),

@@ -236,7 +236,8 @@ __global__ void label_embed_bwd_kernel(const float* __restrict__ dc, const int64
 // ==================================================================== layout kernels
 // patches[(b,t), (c,i,j)] = x[b, c, hp*p + i, wp*p + j]: the im2col of the patch-embed conv, in the
 // flattened conv-weight order, bf16 (B operand of the patch-embed weight gradient).
-__global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+template <typename TOut>
+__global__ void patchify_kernel(const float* __restrict__ x, TOut* __restrict__ out, int B, int C, int H,
                                 int W, int p) {
   const int Hp = H / p, Wp = W / p, K = C * p * p;
   const size_t n = (size_t)B * Hp * Wp * K;
@@ -247,7 +248,8 @@ __global__ void patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __re
     const int hp = t / Wp, wp = t - hp * Wp;
     const int c = k / (p * p), r = k - c * p * p;
     const int i = r / p, j = r - i * p;
-    out[idx] = __float2bfloat16_rn(x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j]);
+    const float v = x[(((size_t)b * C + c) * H + hp * p + i) * W + wp * p + j];
+    if constexpr (sizeof(TOut) == 2) out[idx] = __float2bfloat16_rn(v); else out[idx] = v;
   }
 }
 
@@ -379,12 +381,17 @@ extern "C" int ditb200_label_embed_bwd(const float* dc, const int64_t* y, float*
   return 0;
 }
 
-extern "C" int ditb200_patchify(const float* x, void* patches, int B, int C, int H, int W, int p, void* stream) {
+extern "C" int ditb200_patchify(const float* x, void* patches, int out_dtype, int B, int C, int H, int W, int p,
+                                void* stream) {
   DITB_REQUIRE(x && patches && B > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0, DITB200_EINVAL,
                "patchify: bad argument");
+  DITB_REQUIRE(out_dtype == DITB200_BF16 || out_dtype == DITB200_F32, DITB200_EINVAL, "patchify: bad out_dtype %d", out_dtype);
   const size_t n = (size_t)B * C * H * W;
   const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  patchify_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p);
+  if (out_dtype == DITB200_BF16)
+    patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<__nv_bfloat16*>(patches), B, C, H, W, p);
+  else
+    patchify_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, reinterpret_cast<float*>(patches), B, C, H, W, p);
   DITB_LAUNCH_CHECK("patchify");
   return 0;
 }

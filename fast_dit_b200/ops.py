@@ -428,12 +428,12 @@ def label_embed_bwd(dc, y, dtable):
     return dtable
 
 
-def patchify(x, p: int):
+def patchify(x, p: int, out_dtype=torch.bfloat16):
     lib = _lib_for(x)
     _chk_contig(x)
     B, Cc, H, W = x.shape
-    out = torch.empty((B * (H // p) * (W // p), Cc * p * p), device=x.device, dtype=torch.bfloat16)
-    _call("patchify", lib.ditb200_patchify, _p(x), _p(out), B, Cc, H, W, p, _stream())
+    out = torch.empty((B * (H // p) * (W // p), Cc * p * p), device=x.device, dtype=out_dtype)
+    _call("patchify", lib.ditb200_patchify, _p(x), _p(out), _DT[out_dtype], B, Cc, H, W, p, _stream())
     return out
 
 

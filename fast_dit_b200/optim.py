@@ -24,7 +24,14 @@ class FusedAdamWEMA:
     state_dict()/load_state_dict()/DDP keep working) and attaches the arena to the model, whose forward
     then reads its bf16 GEMM weights from the shadow arena this optimizer maintains."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=0.9999):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, ema_decay=0.9999,
+                 overlap_backward: bool = False):
+        """overlap_backward=True applies the update of every gradient bucket (final layer, each block from last to
+        first, embedders) on a side stream AS SOON AS backward has finished that bucket (after its all-reduce under
+        data parallelism), so the HBM-bound optimizer pass runs underneath the tensor-bound backward GEMMs of the
+        earlier blocks; step() then only joins the streams.  Same arithmetic as backward(); step().  Opt-in, because
+        the parameters already hold the new values when backward() returns: no gradient accumulation over several
+        backward calls and no gradient clipping between backward() and step() in this mode."""
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise L.Ditb200Error("FusedAdamWEMA needs the model on a CUDA device (there is no CPU path)")
@@ -45,8 +52,13 @@ class FusedAdamWEMA:
         self.step_count = 0
         self._views = None
         self._versions = None
+        self.overlap_backward = bool(overlap_backward)
+        self._side = None          # stream the early updates run on
+        self._applied = None       # bucket keys already updated in the step that is being built (None: no step open)
         model._flat = self
         model._shadow = {}
+        if self.overlap_backward:
+            model._bucket_ready = self._bucket_ready
         self.refresh()
 
     # ------------------------------------------------------------------ what the model's forward reads
@@ -86,11 +98,55 @@ class FusedAdamWEMA:
         return self._views
 
     # ------------------------------------------------------------------------------------ the step
+    def _update(self, grads, lo, hi):
+        """The fused AdamW + EMA + bf16-shadow pass over arena elements [lo, hi)."""
+        sl = slice(lo, hi)
+        ops.adamw_ema(self.flat[sl], grads[sl], self.exp_avg[sl], self.exp_avg_sq[sl],
+                      self.ema[sl] if self.ema is not None else None, self.shadow[sl] if self.shadow is not None else None,
+                      lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
+                      step=self.step_count, ema_decay=self.ema_decay if self.ema is not None else 0.0)
+
+    @torch.no_grad()
+    def _bucket_ready(self, key, arena, after=None):
+        """Called by the model's backward when bucket `key` is final (key None: backward is over).  `after`: what
+        must run on the update stream first — the data-parallel wrapper's wait for the bucket's all-reduce."""
+        m = self.model
+        if arena is not getattr(m, "_grad_arena", None):  # a scratch arena: the caller is accumulating gradients
+            raise L.Ditb200Error("FusedAdamWEMA(overlap_backward=True) updates during backward: call "
+                                 "zero_grad(set_to_none=True) between steps (no gradient accumulation in this mode)")
+        cur = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        if key is None:
+            cur.wait_stream(self._side)  # whatever follows backward sees the gradients averaged and the weights updated
+            return
+        if self._applied is None:
+            if self._versions != self._snapshot():
+                self.refresh()
+            self.step_count += 1
+            self._applied = set()
+        self._side.wait_stream(cur)  # the bucket's last gradient kernel has been queued on `cur`
+        with torch.cuda.stream(self._side):
+            for fn in after or ():
+                fn()
+            for lo, hi in self.layout.buckets[key]:
+                self._update(arena.flat, lo, hi)
+        self._applied.add(key)
+
     @torch.no_grad()
     def step(self):
         m = self.model
         if getattr(m, "_flat", None) is not self:
             raise L.Ditb200Error("the model's parameters were moved after FusedAdamWEMA was built; rebuild the optimizer")
+        if self._applied is not None:  # updates were applied during backward: finish what is left and join
+            arena = m._grad_arena
+            torch.cuda.current_stream().wait_stream(self._side)
+            for key, slices in self.layout.buckets.items():
+                if key not in self._applied:
+                    for lo, hi in slices:
+                        self._update(arena.flat, lo, hi)
+            self._applied = None
+            return
         arena = getattr(m, "_grad_arena", None)
         if arena is None:
             arena = GradArena(m)

@@ -145,28 +145,34 @@ class DataParallel(torch.nn.Module):
     def _sync(self, key, arena):
         import torch.distributed as dist
 
+        def finish(work, buf, avg_done):
+            work.wait()  # the CURRENT stream waits for the collective
+            if isinstance(avg_done, torch.Tensor):  # bf16 wire format: refill the f32 arena slice
+                if avg_done.is_cuda:
+                    avg_done.record_stream(torch.cuda.current_stream())  # may be the optimizer's update stream
+                buf.copy_(avg_done)
+            elif not avg_done:
+                buf.div_(self.world)
+
         if key is None:  # end of backward: the compute stream must see every reduced bucket
             for work, buf, avg_done in self._pending:
-                work.wait()
-                if isinstance(avg_done, torch.Tensor):  # bf16 wire format: refill the f32 arena slice
-                    buf.copy_(avg_done)
-                elif not avg_done:
-                    buf.div_(self.world)
+                finish(work, buf, avg_done)
             self._pending = []
             if self._dynamic_prev is not None:
                 from . import ops
 
                 ops.set_gemm_dynamic(self._dynamic_prev)
                 self._dynamic_prev = None
-            return
+            return None
         self.buckets_issued.append(key)
         if self.world == 1:
-            return
+            return None
         if self.dynamic_gemm and self._dynamic_prev is None and arena.bucket(key)[0].is_cuda:
             # from the first collective to the end of backward the GEMMs share the SMs with NCCL's CTAs
             from . import ops
 
             self._dynamic_prev = ops.set_gemm_dynamic(True)
+        first = len(self._pending)
         for buf in arena.bucket(key):
             if buf.is_cuda and self.grad_dtype == torch.bfloat16:
                 from . import ops
@@ -180,6 +186,12 @@ class DataParallel(torch.nn.Module):
             else:            # gloo (CPU tests of the host logic): sum, divide afterwards
                 work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
                 self._pending.append((work, buf, False))
+        if getattr(self.module, "_bucket_ready", None) is not None:
+            # an optimizer that updates during backward takes the bucket over: it waits for these collectives on ITS
+            # stream, finishes the averaging there and applies the update (training._DiTFunction.backward's sync())
+            mine, self._pending = self._pending[first:], self._pending[:first]
+            return [lambda w=w, b=b, a=a: finish(w, b, a) for (w, b, a) in mine]
+        return None
 
     def forward(self, *args, **kwargs):
         self.buckets_issued = []

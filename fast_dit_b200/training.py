@@ -256,7 +256,16 @@ class _DiTFunction(torch.autograd.Function):
         bf = torch.bfloat16
         arena = _arena_for(model)
         G = arena.view
-        sync = getattr(model, "_grad_sync", None)  # parallel.DataParallel: called as each bucket completes
+        def sync(key, arena):
+            """A bucket's gradients are final: hand it to the data-parallel wrapper (all-reduce issued at once,
+            parallel.DataParallel) and to an optimizer that updates during backward (optim.FusedAdamWEMA with
+            overlap_backward=True; it runs after the bucket's collective)."""
+            reduce = getattr(model, "_grad_sync", None)
+            after = reduce(key, arena) if reduce is not None else None
+            ready = getattr(model, "_bucket_ready", None)
+            if ready is not None:
+                ready(key, arena, after)
+
         w = sh["w"]
         ada_w = sh["ada_w"]
         dsc = torch.zeros((N, D), device=dev, dtype=torch.float32)  # gradient of silu(c), summed over all adaLN layers
@@ -283,8 +292,7 @@ class _DiTFunction(torch.autograd.Function):
         ops.ln_modulate_bwd(dhf, tok_final, mf[:, D:], stf, T, dtok, False, dmod_f[:, :D], dmod_f[:, D:])
         ada_bwd(dmod_f, ada_w[Ld * 6 * D:], fl.adaLN_modulation[1])
         del dz, hf, dhf
-        if sync is not None:
-            sync("final_layer", arena)
+        sync("final_layer", arena)
 
         # ---------------- blocks, last to first (models_original.py:118-122)
         for i in range(Ld - 1, -1, -1):
@@ -317,8 +325,7 @@ class _DiTFunction(torch.autograd.Function):
             ops.ln_modulate_bwd(dh, x_in, sc1, st1, T, dtok, True, dm[0], dm[1])
             ada_bwd(dmod, ada_w[i * 6 * D:(i + 1) * 6 * D], blk.adaLN_modulation[1])
             del dy1, do, dqkv, dh
-            if sync is not None:
-                sync(f"blocks.{i}", arena)
+            sync(f"blocks.{i}", arena)
 
         # ---------------- embedders (models_original.py:240-243)
         pe = model.x_embedder.proj
@@ -334,9 +341,8 @@ class _DiTFunction(torch.autograd.Function):
         dpre = ops.silu_bwd(dh1, pre1)
         ops.gemm(ops.cast_bf16(dpre), ops.cast_bf16(t_freq), None, out=G(te.mlp[0].weight), trans_a=True, trans_w=True)
         ops.colsum(dpre, out=G(te.mlp[0].bias))
-        if sync is not None:
-            sync("embed", arena)
-            sync(None, arena)  # all buckets issued: make the compute stream wait for the collectives
+        sync("embed", arena)
+        sync(None, arena)  # all buckets issued: make the compute stream wait for the collectives / the early updates
 
         grads = [arena.view(q) if q.requires_grad else None for q in model.parameters()]
         assert len(grads) == ctx.n_params

@@ -173,9 +173,10 @@ int ditb200_colsum(const void* in, int dtype, float* out, int accumulate, int R,
 int ditb200_label_embed_bwd(const float* dc, const int64_t* y, float* dtable, int B, int D, int num_rows,
                             void* stream);
 
-/* patches[B*T, C*p*p] bf16 = im2col of x[B,C,H,W] f32 in the conv-weight order (c, i, j): the
- * token-major operand of the patch-embed weight gradient (backward of timm PatchEmbed.proj). */
-int ditb200_patchify(const float* x, void* patches, int B, int C, int H, int W, int p, void* stream);
+/* patches[B*T, C*p*p] (out_dtype: bf16 or f32) = im2col of x[B,C,H,W] f32 in the conv-weight order (c, i, j): the
+ * token-major operand of the patch-embed weight gradient (backward of timm PatchEmbed.proj), and the A operand
+ * of a wide patch embedding run as a GEMM (the fork's dino_embedder, C = 768: /root/reference/models.py:652,744). */
+int ditb200_patchify(const float* x, void* patches, int out_dtype, int B, int C, int H, int W, int p, void* stream);
 
 /* dz[B*T, p*p*Cout] bf16 = inverse of DiT.unpatchify (models_original.py:218-231) applied to the
  * gradient dout[B, Cout, Hp*p, Hp*p] f32 of the model output; T = Hp*Hp. */

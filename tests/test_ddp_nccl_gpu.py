@@ -45,15 +45,15 @@ def _worker(rank, world, port, q):
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
         res = {}
-        for wire in (torch.float32, torch.bfloat16):
+        for wire, overlap in ((torch.float32, False), (torch.bfloat16, False), (torch.float32, True), (torch.bfloat16, True)):
             torch.manual_seed(7 * world + rank)  # rank-dependent initial weights
             m = DiT_models["DiT-S/4"](input_size=32, num_classes=1000, precision="bf16")
             rerandomise_zero_params(m, seed=1234 + rank)
             m = m.to(dev).train()
-            opt = FusedAdamWEMA(m, lr=1e-3, weight_decay=0.0, ema_decay=0.99)
+            opt = FusedAdamWEMA(m, lr=1e-3, weight_decay=0.0, ema_decay=0.99, overlap_backward=overlap)
             before = m.blocks[0].attn.qkv.weight.detach().clone()
             net = DataParallel(m, grad_dtype=wire)
-            tag = "f32" if wire == torch.float32 else "bf16"
+            tag = ("f32" if wire == torch.float32 else "bf16") + ("+overlap" if overlap else "")
             # ---- replicas agree after construction
             flat = opt.flat.clone()
             ref = flat.clone()
@@ -69,14 +69,20 @@ def _worker(rank, world, port, q):
             y = torch.randint(0, 1000, (4,), device=dev, generator=g)
             dout = torch.randn(4, 8, 32, 32, device=dev, generator=g)
             m.eval()  # no label dropout: both passes see the same labels
+            # (the wrapper and an overlapping optimizer install their bucket hooks on the module itself)
+            hooks = (m._grad_sync, getattr(m, "_bucket_ready", None))
+            m._grad_sync = m._bucket_ready = None
             m(x, t, y).backward(dout)
+            m._grad_sync, m._bucket_ready = hooks
             alone = torch.cat([p.grad.flatten().float() for p in m.parameters() if p.grad is not None])
             mean = alone.clone()
             dist.all_reduce(mean, op=dist.ReduceOp.SUM)
             mean /= world
             m.zero_grad(set_to_none=True)
+            w_before = opt.flat.clone()
             net(x, t, y).backward(dout)
             torch.cuda.synchronize()
+            res[tag + ".updated_during_backward"] = bool(not torch.equal(w_before, opt.flat))
             got = torch.cat([p.grad.flatten().float() for p in m.parameters() if p.grad is not None])
             res[tag + ".grad_vs_mean"] = _rel(got, mean)
             res[tag + ".grad_vs_alone"] = _rel(got, alone)  # must NOT be small: the shards differ
@@ -118,7 +124,8 @@ def test_data_parallel_over_nccl_two_ranks():
         res = out[rank]
         assert "error" not in res, res.get("error")
         print(f"rank {rank}: " + ", ".join(f"{k}={v if isinstance(v, bool) else f'{v:.2e}'}" for k, v in res.items()))
-        for tag, tol in (("f32", 2e-3), ("bf16", 8e-3)):
+        for tag, tol in (("f32", 2e-3), ("bf16", 8e-3), ("f32+overlap", 2e-3), ("bf16+overlap", 8e-3)):
+            assert res[f"{tag}.updated_during_backward"] is tag.endswith("overlap"), (rank, tag)
             for k in ("weights_equal_rank0", "weights_changed_on_nonzero_rank", "shadow_matches", "ema_matches",
                       "weights_equal_after_step", "ema_equal_after_step"):
                 assert res[f"{tag}.{k}"] is True, (rank, tag, k)

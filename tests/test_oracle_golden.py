@@ -122,3 +122,37 @@ def test_oracle_sample_loop_matches_reference_trajectory():
                                       z.shape, z, noise, clip_denoised=False, model_kwargs=dict(y=y))
     for i, s in enumerate(traj):
         assert rel_l2(s, fx["traj"][i]) < 1e-5, i
+
+
+def _fork_case(tag):
+    """Inputs of a dit_fork_*.npz fixture: the large dino_feat tensor is replayed from the stored generator seed."""
+    fx = golden(f"dit_{tag}.npz")
+    kw = {k[3:]: fx[k].item() for k in fx.files if k.startswith("kw.")}
+    g = torch.Generator().manual_seed(int(fx["gen_seed"]))
+    n, lat = fx["x"].shape[0], kw["input_size"]
+    x = torch.randn(n, 4, lat, lat, generator=g)
+    dino = torch.randn(n, kw["dino_feat_size"], lat, lat, generator=g)
+    assert np.array_equal(x.numpy(), fx["x"]) and abs(float(dino.double().sum()) - float(fx["dino_sum"])) < 1e-6
+    return fx, kw, x, dino, torch.from_numpy(fx["t"]), torch.from_numpy(fx["y"])
+
+
+@pytest.mark.parametrize("tag", ["fork_small", "fork_p4"])
+def test_oracle_fork_dino_variant(tag):
+    """oracle/dit_dino_oracle.py against the UNMODIFIED fork model (/root/reference/models.py: 9-chunk adaLN, DINO
+    cross-attention in the 14th and 16th block, c = t), and the product module's construction: same parameter count,
+    same state_dict keys, bit-identical initial weights under the same seed."""
+    from fast_dit_b200.models_dino import DiT, DiT_models
+    from oracle.dit_dino_oracle import dit_dino_forward
+
+    fx, kw, x, dino, t, y = _fork_case(tag)
+    torch.manual_seed(0)
+    m = DiT(**kw)
+    O.rerandomise_zero_params(m.named_parameters())
+    m.eval()
+    check_checksums(m, fx)
+    assert sum(p.numel() for p in m.parameters()) == int(fx["nparams"])
+    cfg = O.DiTConfig(**{k: v for k, v in kw.items() if k != "dino_feat_size"})
+    with torch.no_grad():
+        out = dit_dino_forward(m.state_dict(), cfg, x, t, dino, y)
+    assert rel_l2(out, fx["out"]) < 1e-6
+    assert sorted(DiT_models) == sorted(f"DiT-{s}/{p}" for s in ("S", "B", "L", "XL") for p in (2, 4, 8))

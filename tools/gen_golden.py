@@ -259,6 +259,61 @@ def gen_diffusion_api():
     print("diffusion_api", len(d))
 
 
+def import_fork_models():
+    """The fork's top-level models.py, UNMODIFIED, imported with empty stand-ins for the visualisation libraries it
+    pulls in at module import (umap, cv2, matplotlib: SURVEY.md §0.1) and oracle/timm_standin for timm."""
+    import importlib.util
+    import types
+
+    for name in ("umap", "cv2", "matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:  # noqa: BLE001
+                sys.modules[name] = types.ModuleType(name)
+    spec = importlib.util.spec_from_file_location("ref_fork_models", os.path.join(REF, "models.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_fork_dino():
+    """the fork's DINO cross-attention DiT (models.py:506-601, 624-754): 9-chunk adaLN,
+    CrossAttention (LayerNorm on q and k, fused kv Linear without bias) in the 14th and 16th block, c = t only.
+    forward(x, t, dino_feat, y) in eval mode (dropout off) on a 16-block model."""
+    import contextlib
+    import io
+
+    FK = import_fork_models()
+    for tag, kw, n in [("fork_small", dict(input_size=32, patch_size=2, hidden_size=384, depth=16, num_heads=6,
+                                            dino_feat_size=64, num_classes=10), 3),
+                       ("fork_p4", dict(input_size=32, patch_size=4, hidden_size=768, depth=16, num_heads=12,
+                                         dino_feat_size=768, num_classes=10), 2)]:
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints per block
+            m = FK.DiT(**kw)
+        rerandomise_zero_params(m.named_parameters())
+        m.eval()
+        g = torch.Generator().manual_seed(21)
+        lat = kw["input_size"]
+        x = torch.randn(n, 4, lat, lat, generator=g)
+        dino = torch.randn(n, kw["dino_feat_size"], lat, lat, generator=g)
+        t = torch.randint(0, 1000, (n,), generator=g)
+        y = torch.randint(0, 10, (n,), generator=g)
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            out = m(x, t, dino, y)
+            out_nodino_blocks = None
+        # dino_feat is large (n x 768 x 32 x 32): the fixture keeps the generator seed; tests replay the draws
+        # (x first, then dino_feat) and check x against the stored copy
+        d = dict(x=x.numpy(), gen_seed=np.array(21), t=t.numpy(), y=y.numpy(), out=out.numpy(),
+                 dino_sum=np.array(float(dino.double().sum())))
+        d.update({"kw." + k: np.array(v) for k, v in kw.items()})
+        d.update(checksums(m))
+        d["nparams"] = np.array(sum(p.numel() for p in m.parameters()))
+        np.savez_compressed(os.path.join(OUT, f"dit_{tag}.npz"), **d)
+        print(tag, "params", int(d["nparams"]), "out std", float(out.std()), "keys", len(m.state_dict()))
+
+
 def gen_sample_loop(model):
     """BASELINE.json configs[0]: DiT-S/2, 10-step CFG-4.0 sampling (n=2 kept images, batch 4 with the
     null-class half), every step's noise drawn from its own seeded CPU generator."""
@@ -293,11 +348,15 @@ def gen_sample_loop(model):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the fixture added in round 2
+    if len(sys.argv) > 1 and sys.argv[1] == "api":  # only the fixtures added in round 2
         gen_diffusion_api()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fork":
+        gen_fork_dino()
         sys.exit(0)
     gen_tables()
     gen_diffusion_api()
+    gen_fork_dino()
     gen_tiny()
     gen_diffusion_kat()
     s2 = gen_seeded("DiT-S/2", 32, 4, "s2_seed0")
