@@ -407,7 +407,7 @@ def run_train(args):
     model = DiT_models[name](input_size=lat, num_classes=1000, precision="bf16")
     rerandomise_zero_params(model)
     model = model.to(dev).train()
-    opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999, overlap_backward=not args.no_overlap_opt)
+    opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999, overlap_backward=args.overlap_opt)
     gdt = torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32
     net = DataParallel(model, grad_dtype=gdt) if world > 1 else model
     diffusion = create_diffusion("")
@@ -489,7 +489,7 @@ def run_train(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{name} {lat}x{lat}x4 latent training step, {n} images/GPU (global batch {n * world}), "
                                "MSE + learned-sigma VLB loss, fused AdamW + EMA"
-                               f"{'' if args.no_overlap_opt else ' (applied per bucket underneath backward)'}, random-init weights",
+                               f"{' (applied per bucket underneath backward)' if args.overlap_opt else ''}, random-init weights",
                    "step_is": "one optimizer step", "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no flush needed",
                    "parallelism": f"dp{world}, per-block gradient all-reduce (NCCL, {args.grad_dtype}, mean) overlapped with backward"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -516,9 +516,9 @@ def main():
     ap.add_argument("--ref-images", type=int, default=0,
                     help="kept images per reference step (0: the workload's, halved until the run fits ~200 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap-opt", action="store_true",
-                    help="training workloads: run the fused AdamW+EMA pass after backward instead of bucket by bucket "
-                         "underneath it (FusedAdamWEMA(overlap_backward=...))")
+    ap.add_argument("--overlap-opt", action="store_true",
+                    help="training workloads: apply the fused AdamW+EMA pass bucket by bucket underneath backward "
+                         "(FusedAdamWEMA(overlap_backward=True)) instead of after it")
     ap.add_argument("--grad-dtype", default="f32", choices=["f32", "bf16"],
                     help="training workloads, N > 1: wire format of the gradient all-reduce (f32 = the reference's DDP)")
     args = ap.parse_args()

@@ -414,6 +414,8 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  DITB_PDL_TRIGGER();
+  DITB_PDL_WAIT();
 
   if (warp == 8) {
     // ================================================================== TMA producer
@@ -710,6 +712,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv0, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  DITB_PDL_TRIGGER();
+  DITB_PDL_WAIT();
   const uint32_t RA = tmem_base, RB = tmem_base + 256;  // S / dP regions
 
   if (warp == 8) {
@@ -979,7 +983,7 @@ int launch_attn_bwd_tc(const void* qkv, const void* dout, const float* lse, cons
   int grid = num_sms();
   if (grid > B * H) grid = B * H;
   const float scale = (float)(1.0 / sqrt((double)hd));
-  attn_bwd_tc_kernel<<<grid, kAtThreads, AttnBwdSmem::kBytes, st>>>(mq0, mq1, md0, md1, lse, dsum,
+  DITB_KLAUNCH(attn_bwd_tc_kernel, dim3(grid), dim3(kAtThreads), AttnBwdSmem::kBytes, st, mq0, mq1, md0, md1, lse, dsum,
                                                                    reinterpret_cast<__nv_bfloat16*>(dqkv), B, H, hd, scale,
                                                                    scale * 1.4426950408889634f);
   DITB_LAUNCH_CHECK("attention_bwd(tcgen05)");
@@ -1014,7 +1018,7 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
     }
     int items = B * H * (T / 256), g = num_sms();
     if (g > items) g = items;
-    attn_fwd_tc_kv_kernel<<<g, kAtThreads, AttnKvSmem::kBytes, st>>>(mq0, mv0, mq1, reinterpret_cast<__nv_bfloat16*>(out),
+    DITB_KLAUNCH(attn_fwd_tc_kv_kernel, dim3(g), dim3(kAtThreads), AttnKvSmem::kBytes, st, mq0, mv0, mq1, reinterpret_cast<__nv_bfloat16*>(out),
                                                                     lse, B, T, H, hd, scale_log2e);
     DITB_LAUNCH_CHECK("attention_fwd(tcgen05, kv)");
     return 0;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_rows_kernel(
     const TDh* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale, int mod_stride,
     const float* __restrict__ stats, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
     float* __restrict__ dscale, int dmod_stride, int T) {
+  DITB_PDL_WAIT();
   constexpr int D = NV * 128;
   __shared__ float red[2 * D];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,6 +173,7 @@ __global__ void gate_resid_bwd_kernel(const float* __restrict__ dxo, const TY* _
                                       const float* __restrict__ gate, int gate_stride, TY* __restrict__ dy,
                                       float* __restrict__ dgate, int dgate_stride, float* __restrict__ dbias, int T,
                                       int D) {
+  DITB_PDL_WAIT();
   const int b = blockIdx.y;
   const int c = (blockIdx.z * blockDim.x + threadIdx.x) * 4;
   if (c >= D) return;
@@ -203,14 +205,85 @@ __global__ void gate_resid_bwd_kernel(const float* __restrict__ dxo, const TY* _
 }
 
 // ======================================================================== column sums
-constexpr int kCsRows = 64;
+// out[c] += sum_r in[r, c]: bias gradients of the QKV / fc1 Linears (HBM-bound: every element is read once).
+// A block owns kCsCols consecutive columns x kCsRows rows: lane l of every warp owns kCsVec consecutive columns
+// (16-byte loads for bf16, 2 x 16 for f32), the block's 8 warps take interleaved rows with 8 loads in flight per
+// lane, the warps' partial sums meet in shared memory and the block issues ONE vector atomic per 4 columns.
+constexpr int kCsRows = 256, kCsVec = 8, kCsCols = 32 * kCsVec, kCsWarps = 8;
+template <typename TIn> struct CsRaw;
+template <> struct CsRaw<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p) : "memory");
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4) : "memory");
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void add_to(float (&acc)[8]) const {
+    acc[0] += a.x, acc[1] += a.y, acc[2] += a.z, acc[3] += a.w, acc[4] += b.x, acc[5] += b.y, acc[6] += b.z, acc[7] += b.w;
+  }
+};
+template <> struct CsRaw<__nv_bfloat16> {
+  uint4 pk;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
+    // pinned (volatile + memory clobber): the batch of loads stays a batch instead of being sunk to its first use
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "l"(p) : "memory");
+  }
+  __device__ __forceinline__ void zero() { pk = make_uint4(0u, 0u, 0u, 0u); }
+  __device__ __forceinline__ void add_to(float (&acc)[8]) const {
+    // bf16 -> f32 is a 16-bit shift: low half = element 0, high half = element 1
+    acc[0] += __uint_as_float(pk.x << 16), acc[1] += __uint_as_float(pk.x & 0xffff0000u);
+    acc[2] += __uint_as_float(pk.y << 16), acc[3] += __uint_as_float(pk.y & 0xffff0000u);
+    acc[4] += __uint_as_float(pk.z << 16), acc[5] += __uint_as_float(pk.z & 0xffff0000u);
+    acc[6] += __uint_as_float(pk.w << 16), acc[7] += __uint_as_float(pk.w & 0xffff0000u);
+  }
+};
 template <typename TIn>
-__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in, float* __restrict__ out, int R, int C) {
+__global__ void __launch_bounds__(32 * kCsWarps, 4) colsum_kernel(const TIn* __restrict__ in, float* __restrict__ out, int R, int C) {
+  DITB_PDL_WAIT();
+  __shared__ float part[kCsWarps][kCsCols];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kCsCols + lane * kCsVec;
+  const int r0 = blockIdx.y * kCsRows, r1 = min(R, r0 + kCsRows);
+  float acc[kCsVec];
+#pragma unroll
+  for (int j = 0; j < kCsVec; ++j) acc[j] = 0.f;
+  if (c < C) {  // C % 8 == 0 on this path: a lane's 8 columns are all inside or all outside
+    constexpr int kBatch = sizeof(TIn) == 2 ? 8 : 4;  // rows (128 bytes per lane) requested before the first is consumed
+    for (int rr = r0 + warp; rr < r1; rr += kBatch * kCsWarps) {
+      CsRaw<TIn> raw[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int r = rr + u * kCsWarps;
+        if (r < r1) raw[u].load(in + (size_t)r * C + c); else raw[u].zero();
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) raw[u].add_to(acc);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kCsVec; ++j) part[warp][lane * kCsVec + j] = acc[j];
+  __syncthreads();
+  const int col = threadIdx.x * 4;  // 64 threads finish the block's 256 columns, 4 each
+  if (col < kCsCols && blockIdx.x * kCsCols + col < C) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < kCsWarps; ++w) {
+      const float4 p4 = *reinterpret_cast<const float4*>(&part[w][col]);
+      s.x += p4.x, s.y += p4.y, s.z += p4.z, s.w += p4.w;
+    }
+    atomicAdd(reinterpret_cast<float4*>(out + blockIdx.x * kCsCols + col), s);  // one 128-bit reduction
+  }
+}
+
+// columns not a multiple of 8 (C % 4 == 0): the 4-columns-per-thread form
+constexpr int kCs4Rows = 64;
+template <typename TIn>
+__global__ void __launch_bounds__(256) colsum4_kernel(const TIn* __restrict__ in, float* __restrict__ out, int R, int C) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c >= C) return;
-  const int r0 = blockIdx.y * kCsRows, r1 = min(R, r0 + kCsRows);
+  const int r0 = blockIdx.y * kCs4Rows, r1 = min(R, r0 + kCs4Rows);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int rr = r0; rr < r1; rr += 8) {  // 8 rows of loads in flight per thread
+  for (int rr = r0; rr < r1; rr += 8) {
     float4 v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -218,7 +291,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ in,
 #pragma unroll
     for (int u = 0; u < 8; ++u) a.x += v[u].x, a.y += v[u].y, a.z += v[u].z, a.w += v[u].w;
   }
-  atomicAdd(reinterpret_cast<float4*>(out + c), a);  // one 128-bit reduction
+  atomicAdd(reinterpret_cast<float4*>(out + c), a);
 }
 
 // ================================================================ label embed, backward
@@ -299,11 +372,11 @@ extern "C" int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float
 #define LNB_CASE(NV)                                                                                             \
   case NV:                                                                                                       \
     if (dh_dtype == DITB200_BF16)                                                                                \
-      ln_modulate_bwd_rows_kernel<NV, __nv_bfloat16><<<rgrid, 128, 0, st>>>(                                     \
+      DITB_KLAUNCH((ln_modulate_bwd_rows_kernel<NV, __nv_bfloat16>), rgrid, dim3(128), 0, st,                    \
           reinterpret_cast<const __nv_bfloat16*>(dh), x, scale, mod_stride, stats, dx, accumulate, dshift, dscale, \
           dmod_stride, T);                                                                                       \
     else                                                                                                         \
-      ln_modulate_bwd_rows_kernel<NV, float><<<rgrid, 128, 0, st>>>(reinterpret_cast<const float*>(dh), x, scale, \
+      DITB_KLAUNCH((ln_modulate_bwd_rows_kernel<NV, float>), rgrid, dim3(128), 0, st, reinterpret_cast<const float*>(dh), x, scale, \
                                                                    mod_stride, stats, dx, accumulate, dshift,    \
                                                                    dscale, dmod_stride, T);                      \
     break;
@@ -344,11 +417,11 @@ extern "C" int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_
   dim3 grid((T + kGrRows - 1) / kGrRows, B, (D / 4 + threads - 1) / threads);
   cudaStream_t st = (cudaStream_t)stream;
   if (y_dtype == DITB200_BF16)
-    gate_resid_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(
+    DITB_KLAUNCH((gate_resid_bwd_kernel<__nv_bfloat16>), grid, dim3(threads), 0, st,
         dx_out, reinterpret_cast<const __nv_bfloat16*>(y), gate, gate_stride, reinterpret_cast<__nv_bfloat16*>(dy),
         dgate, dgate_stride, dbias, T, D);
   else
-    gate_resid_bwd_kernel<float><<<grid, threads, 0, st>>>(dx_out, reinterpret_cast<const float*>(y), gate, gate_stride,
+    DITB_KLAUNCH((gate_resid_bwd_kernel<float>), grid, dim3(threads), 0, st, dx_out, reinterpret_cast<const float*>(y), gate, gate_stride,
                                                           reinterpret_cast<float*>(dy), dgate, dgate_stride, dbias, T, D);
   DITB_LAUNCH_CHECK("gate_resid_bwd");
   return 0;
@@ -363,11 +436,19 @@ extern "C" int ditb200_colsum(const void* in, int dtype, float* out, int accumul
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st);
     if (e != cudaSuccess) return check_cuda(e, "colsum memset");
   }
-  dim3 grid((C / 4 + 255) / 256, (R + kCsRows - 1) / kCsRows);
-  if (dtype == DITB200_BF16)
-    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, R, C);
-  else
-    colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), out, R, C);
+  if (C % 8 == 0) {
+    dim3 grid((C + kCsCols - 1) / kCsCols, (R + kCsRows - 1) / kCsRows);
+    if (dtype == DITB200_BF16)
+      DITB_KLAUNCH((colsum_kernel<__nv_bfloat16>), grid, dim3(32 * kCsWarps), 0, st, reinterpret_cast<const __nv_bfloat16*>(in), out, R, C);
+    else
+      DITB_KLAUNCH((colsum_kernel<float>), grid, dim3(32 * kCsWarps), 0, st, reinterpret_cast<const float*>(in), out, R, C);
+  } else {
+    dim3 grid((C / 4 + 255) / 256, (R + kCs4Rows - 1) / kCs4Rows);
+    if (dtype == DITB200_BF16)
+      colsum4_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, R, C);
+    else
+      colsum4_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), out, R, C);
+  }
   DITB_LAUNCH_CHECK("colsum");
   return 0;
 }

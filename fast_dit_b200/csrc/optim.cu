@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float4* __restrict__ p, 
                                                         float4* __restrict__ m, float4* __restrict__ v,
                                                         float4* __restrict__ ema, uint2* __restrict__ shadow,
                                                         size_t n4, const AdamArgs a) {
+  DITB_PDL_WAIT();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 gv = ldg_stream_f4(g + i);
@@ -68,7 +69,7 @@ extern "C" int ditb200_adamw_ema(float* param, const float* grad, float* exp_avg
   const size_t n4 = n / 4;
   int blocks = num_sms() > 0 ? num_sms() * 8 : 1184;
   if ((size_t)blocks * 256 > n4) blocks = (int)((n4 + 255) / 256);
-  adamw_ema_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  DITB_KLAUNCH(adamw_ema_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
       reinterpret_cast<float4*>(exp_avg_sq), reinterpret_cast<float4*>(ema), reinterpret_cast<uint2*>(shadow_bf16), n4, a);
   DITB_LAUNCH_CHECK("adamw_ema");

@@ -461,10 +461,17 @@ def test_optimizer_checkpoint_round_trip_and_torch_adamw_interchange(dev):
     assert ck["opt"]["state"][1]["exp_avg"].data_ptr() != opt.exp_avg.data_ptr()  # copies, not live views
     assert 0 not in ck["opt"]["state"], "pos_embed is parameter 0 of model.parameters() and frozen: no state"
     grads(m, 3)
+    # the weight gradients are accumulated with f32 atomics (run-to-run spread ~1e-3): the resumed runs below are fed
+    # THESE gradients, so that what is compared is the optimizer state, not the backward pass
+    g3 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
     opt.step()
     opt.zero_grad()
     want_w = {k: v.clone() for k, v in m.state_dict().items()}
     want_ema = opt.ema_state_dict()
+
+    def feed(model):
+        for k, p in model.named_parameters():
+            p.grad = g3[k].clone() if k in g3 else None
 
     # (i) resume in a fresh process' worth of objects
     m2 = build_product_model("DiT-S/8", input_size=32, num_classes=1000, precision="bf16", seed=5).cuda().train()
@@ -474,7 +481,7 @@ def test_optimizer_checkpoint_round_trip_and_torch_adamw_interchange(dev):
     assert opt2.step_count == 2 and opt2.lr == 2e-3 and opt2.weight_decay == 0.01
     for k, v in opt2.ema_state_dict().items():
         assert torch.equal(v, ck["ema"][k]), k
-    grads(m2, 3)
+    feed(m2)
     opt2.step()
     for k, v in m2.state_dict().items():
         assert rel_l2(v, want_w[k]) < 1e-6, k
@@ -490,9 +497,8 @@ def test_optimizer_checkpoint_round_trip_and_torch_adamw_interchange(dev):
     m3.load_state_dict(ck["model"])
     opt3 = FusedAdamWEMA(m3, ema_decay=None)
     opt3.load_state_dict(topt.state_dict())  # torch's own dict: no "ema", no "param_names"
-    grads(m3, 3)
-    for p, q in zip(m3.parameters(), ref.parameters()):
-        q.grad = None if p.grad is None else p.grad.clone()
+    feed(m3)
+    feed(ref)
     opt3.step()
     topt.step()
     for (k, p), q in zip(m3.named_parameters(), ref.parameters()):
