@@ -98,6 +98,31 @@ def _worker(rank, world, port, q):
             dist.broadcast(ref, src=0)
             res[tag + ".ema_equal_after_step"] = bool(torch.equal(ema, ref))
             del net, opt, m
+        # ---- the reference's own wrapper: torch DistributedDataParallel around this package's DiT
+        # (train_options/train_original.py:149 — INTEGRATION.md says it works unchanged: gradients reach the
+        # parameters through autograd, where DDP's reducer hooks pick them up)
+        torch.manual_seed(3)  # same weights on every rank, so that "alone" can be taken before DDP is built
+        m = DiT_models["DiT-S/4"](input_size=32, num_classes=1000, precision="bf16")
+        rerandomise_zero_params(m)
+        m = m.to(dev).eval()
+        g = torch.Generator(device=dev).manual_seed(200 + rank)
+        x = torch.randn(4, 4, 32, 32, device=dev, generator=g)
+        t = torch.randint(0, 1000, (4,), device=dev, generator=g)
+        y = torch.randint(0, 1000, (4,), device=dev, generator=g)
+        dout = torch.randn(4, 8, 32, 32, device=dev, generator=g)
+        m(x, t, y).backward(dout)
+        alone = torch.cat([p.grad.flatten().float() for p in m.parameters() if p.grad is not None])
+        mean = alone.clone()
+        dist.all_reduce(mean, op=dist.ReduceOp.SUM)
+        mean /= world
+        m.zero_grad(set_to_none=True)
+        ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[local])
+        ddp(x, t, y=y).backward(dout)
+        torch.cuda.synchronize()
+        got = torch.cat([p.grad.flatten().float() for p in m.parameters() if p.grad is not None])
+        res["torch_ddp.grad_vs_mean"] = _rel(got, mean)
+        res["torch_ddp.grad_vs_alone"] = _rel(got, alone)
+        del ddp
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, res))
@@ -133,3 +158,4 @@ def test_data_parallel_over_nccl_two_ranks():
             # the atomically accumulated weight gradients (3e-3 bound used for a single rank in test_backward_gpu.py)
             assert res[f"{tag}.grad_vs_mean"] < tol, (rank, tag, res[f"{tag}.grad_vs_mean"])
             assert res[f"{tag}.grad_vs_alone"] > 0.1, (rank, tag)
+        assert res["torch_ddp.grad_vs_mean"] < 2e-3 and res["torch_ddp.grad_vs_alone"] > 0.1, (rank, res)

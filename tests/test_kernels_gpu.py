@@ -358,3 +358,77 @@ def test_cast_bf16(ops, dev):
     for n in (1, 3, 4, 1027, 1 << 20):
         x = torch.randn(n, device=dev, generator=g)
         assert torch.equal(ops.cast_bf16(x), x.bfloat16())
+
+
+def _guarded(shape, dtype, dev, fill=0.0):
+    """An output tensor carved out of a larger allocation whose head and tail (4 KB each) hold a sentinel pattern: a
+    kernel that writes outside its output corrupts them.  compute-sanitizer is closed on this GPU pool
+    (profiles/r02_sanitizer.md), so out-of-bounds WRITES are hunted this way on ragged shapes."""
+    n = 1
+    for s in shape:
+        n *= s
+    pad = 4096 // torch.empty(0, dtype=dtype).element_size()
+    buf = torch.full((n + 2 * pad,), 12345.0, device=dev, dtype=dtype)
+    out = buf[pad:pad + n].view(shape)
+    out.fill_(fill)
+    return buf, out, pad
+
+
+def _guards_intact(buf, pad):
+    return bool((buf[:pad] == 12345.0).all()) and bool((buf[-pad:] == 12345.0).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 72), (1000, 3456, 1152), (257, 1160, 64), (129, 136, 1152), (8200, 1160, 128)])
+def test_gemm_epilogues_do_not_write_outside_the_output(ops, dev, M, N, K):
+    from fast_dit_b200 import _lib as L
+
+    g = torch.Generator(device=dev).manual_seed(40)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    T = 64
+    gate = torch.randn((M + T - 1) // T, N, device=dev, generator=g)
+    for epi, dt in ((L.EPI_BIAS, torch.bfloat16), (L.EPI_BIAS, torch.float32), (L.EPI_BIAS_GELU, torch.bfloat16),
+                    (L.EPI_BIAS_GATE_RESID, torch.float32)):
+        for kw in ({}, dict(tile_n=256, cta_group=2), dict(tile_n=128, cta_group=1), dict(reverse_m=True)):
+            buf, out, pad = _guarded((M, N), dt, dev)
+            if epi == L.EPI_BIAS_GATE_RESID:
+                ops.gemm(a, w, bias, epilogue=epi, resid=out, gate=gate, rows_per_gate=T, **kw)
+            else:
+                ops.gemm(a, w, bias, epilogue=epi, out=out, **kw)
+            torch.cuda.synchronize()
+            assert _guards_intact(buf, pad), (epi, dt, kw)
+            assert torch.isfinite(out.float()).all()
+    # weight gradient: split-K with f32 atomics into an accumulating output
+    dy = torch.randn(M, N, device=dev, generator=g).bfloat16()
+    buf, out, pad = _guarded((N, K), torch.float32, dev)
+    ops.gemm(dy, a, None, out=out, trans_a=True, trans_w=True, split_k=3)
+    torch.cuda.synchronize()
+    assert _guards_intact(buf, pad)
+    assert rel_l2(out, dy.double().t() @ a.double()) < 1e-4
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(3, 128, 5, 72), (2, 256, 16, 72), (1, 512, 3, 72), (2, 100, 3, 72), (3, 64, 12, 64)])
+def test_attention_and_layernorm_do_not_write_outside_their_outputs(ops, dev, B, T, H, hd):
+    g = torch.Generator(device=dev).manual_seed(41)
+    D = H * hd
+    qkv = torch.randn(B * T, 3 * D, device=dev, generator=g).bfloat16()
+    for rev in (False, True):
+        buf, out, pad = _guarded((B * T, D), torch.bfloat16, dev)
+        ops.attention(qkv, B, T, H, hd, out=out, reverse=rev)
+        torch.cuda.synchronize()
+        assert _guards_intact(buf, pad), ("attention", rev)
+        assert rel_l2(out.float(), _attn_ref(qkv.float(), B, T, H, hd)) < 6e-3
+    x = torch.randn(B * T, D, device=dev, generator=g)
+    mod = torch.randn(B, 3 * D, device=dev, generator=g)
+    for dt in (torch.bfloat16, torch.float32):
+        buf, out, pad = _guarded((B * T, D), dt, dev)
+        ops.ln_modulate(x, mod[:, :D], mod[:, D:2 * D], T, out_dtype=dt, out=out, reverse=True)
+        torch.cuda.synchronize()
+        assert _guards_intact(buf, pad), ("ln_modulate", dt)
+    if D in (384, 768, 1024, 1152):
+        y = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+        buf, xo, pad = _guarded((B * T, D), torch.float32, dev)
+        ops.ln_modulate_resid(x, y, mod[:, 2 * D:], mod[:, :D], mod[:, D:2 * D], T, x_out=xo)
+        torch.cuda.synchronize()
+        assert _guards_intact(buf, pad), "ln_modulate_resid"
