@@ -409,7 +409,7 @@ def run_train(args):
     model = model.to(dev).train()
     opt = FusedAdamWEMA(model, lr=1e-4, weight_decay=0.0, ema_decay=0.9999, overlap_backward=args.overlap_opt)
     gdt = torch.bfloat16 if args.grad_dtype == "bf16" else torch.float32
-    net = DataParallel(model, grad_dtype=gdt) if world > 1 else model
+    net = DataParallel(model, grad_dtype=gdt, shard_optimizer=args.shard_opt) if world > 1 else model
     diffusion = create_diffusion("")
     g = torch.Generator().manual_seed(1000 + rank)
     x_h = torch.randn(n, 4, lat, lat, generator=g).pin_memory()
@@ -491,7 +491,10 @@ def run_train(args):
                                "MSE + learned-sigma VLB loss, fused AdamW + EMA"
                                f"{' (applied per bucket underneath backward)' if args.overlap_opt else ''}, random-init weights",
                    "step_is": "one optimizer step", "l2_policy": "activations per step (GBs) exceed the 126 MB L2; no flush needed",
-                   "parallelism": f"dp{world}, per-block gradient all-reduce (NCCL, {args.grad_dtype}, mean) overlapped with backward"},
+                   "parallelism": (f"dp{world}, optimizer state sharded over the ranks: per-block reduce-scatter of the weight "
+                                   "gradients (NCCL, f32, mean) overlapped with backward, 1/N of the AdamW+EMA pass per rank, "
+                                   "all-gather of the bf16 weight shadows" if (args.shard_opt and world > 1) else
+                                   f"dp{world}, per-block gradient all-reduce (NCCL, {args.grad_dtype}, mean) overlapped with backward")},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "mfu_bf16": {"value": value / world * flops_img / 1e12 / tf_peak, "denominator_tflops": tf_peak,
                      "flops_per_image_G": flops_img / 1e9},
@@ -516,6 +519,9 @@ def main():
     ap.add_argument("--ref-images", type=int, default=0,
                     help="kept images per reference step (0: the workload's, halved until the run fits ~200 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-opt", action="store_true",
+                    help="training workloads, N > 1: partition the optimizer state over the ranks (reduce-scatter of the "
+                         "weight gradients, 1/N of the AdamW+EMA pass per rank, all-gather of the bf16 weight shadows)")
     ap.add_argument("--overlap-opt", action="store_true",
                     help="training workloads: apply the fused AdamW+EMA pass bucket by bucket underneath backward "
                          "(FusedAdamWEMA(overlap_backward=True)) instead of after it")

@@ -68,6 +68,7 @@ class FusedAdamWEMA:
     def refresh(self):
         """Re-derive the bf16 shadows from the f32 master weights (after load_state_dict or any edit of
         the parameters that did not go through step())."""
+        self.consolidate()  # sharded state: the non-owned f32 parts must be current first (collective, symmetric)
         if self.shadow is not None:
             ops.cast_bf16(self.flat, out=self.shadow)
         self._versions = self._snapshot()
@@ -98,18 +99,64 @@ class FusedAdamWEMA:
         return self._views
 
     # ------------------------------------------------------------------------------------ the step
-    def _update(self, grads, lo, hi):
-        """The fused AdamW + EMA + bf16-shadow pass over arena elements [lo, hi)."""
+    def _update(self, grads, lo, hi, offset=0):
+        """The fused AdamW + EMA + bf16-shadow pass over arena elements [lo, hi); their gradients are
+        grads[lo - offset : hi - offset] (offset != 0: `grads` is this rank's part of a reduce-scattered region)."""
         sl = slice(lo, hi)
-        ops.adamw_ema(self.flat[sl], grads[sl], self.exp_avg[sl], self.exp_avg_sq[sl],
+        ops.adamw_ema(self.flat[sl], grads[lo - offset:hi - offset], self.exp_avg[sl], self.exp_avg_sq[sl],
                       self.ema[sl] if self.ema is not None else None, self.shadow[sl] if self.shadow is not None else None,
                       lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay,
                       step=self.step_count, ema_decay=self.ema_decay if self.ema is not None else 0.0)
 
+    # ------------------------------------------------------------------ state partitioned over data-parallel ranks
+    def enable_sharding(self, dp):
+        """Called by parallel.DataParallel(shard_optimizer=True): from now on this rank updates only its part of
+        every sharded region (dp.part) and the update runs during backward."""
+        for key, regions in self.layout.big.items():
+            for lo, hi in regions:
+                if (hi - lo) % (dp.world * 64):
+                    raise L.Ditb200Error(f"region {key} [{lo}, {hi}) does not divide into {dp.world} 64-float parts")
+        self._dp = dp
+        self._ag_pending = []
+        self._stale = False  # non-owned parts of flat / moments / ema are out of date
+        self.overlap_backward = True
+        self.model._bucket_ready = self._bucket_ready
+
+        def guard(module, prefix, keep_vars):
+            # the reference saves checkpoints on rank 0 only (train.py:229-239): a collective hidden in state_dict()
+            # would hang there, so ask for the explicit, all-rank consolidate() instead
+            if self._stale:
+                raise L.Ditb200Error("the optimizer state is sharded over the data-parallel ranks: call "
+                                     "opt.consolidate() on EVERY rank before model.state_dict() / opt.state_dict()")
+        self.model.register_state_dict_pre_hook(guard)
+
+    def _require_consolidated(self):
+        if getattr(self, "_dp", None) is not None and self._stale:
+            raise L.Ditb200Error("the optimizer state is sharded over the data-parallel ranks: call opt.consolidate() "
+                                 "on EVERY rank first")
+
     @torch.no_grad()
-    def _bucket_ready(self, key, arena, after=None):
+    def consolidate(self):
+        """Gather every rank's parts of the f32 master weights, the Adam moments and the EMA, so that each rank
+        holds the complete state again (checkpoints, evaluation of the f32 weights).  Collective: all ranks call it."""
+        dp = getattr(self, "_dp", None)
+        if dp is None or not self._stale:
+            return
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        for regions in self.layout.big.values():
+            for lo, hi in regions:
+                for arr in (self.flat, self.exp_avg, self.exp_avg_sq, self.ema):
+                    if arr is not None:
+                        dp.gather_region(arr, lo, hi)
+        self._stale = False
+
+    @torch.no_grad()
+    def _bucket_ready(self, key, arena, after=None, plan=None):
         """Called by the model's backward when bucket `key` is final (key None: backward is over).  `after`: what
-        must run on the update stream first — the data-parallel wrapper's wait for the bucket's all-reduce."""
+        must run on the update stream first — the data-parallel wrapper's wait for the bucket's collectives.  `plan`
+        (sharded optimizer): [("shard" | "full", lo, hi, gradients)] — the regions of the bucket this rank updates a
+        part of / updates whole."""
         m = self.model
         if arena is not getattr(m, "_grad_arena", None):  # a scratch arena: the caller is accumulating gradients
             raise L.Ditb200Error("FusedAdamWEMA(overlap_backward=True) updates during backward: call "
@@ -118,6 +165,10 @@ class FusedAdamWEMA:
         if self._side is None:
             self._side = torch.cuda.Stream()
         if key is None:
+            for w in getattr(self, "_ag_pending", ()):  # the gathered bf16 shadows the next forward reads
+                w.wait()
+            if getattr(self, "_dp", None) is not None:
+                self._ag_pending = []
             cur.wait_stream(self._side)  # whatever follows backward sees the gradients averaged and the weights updated
             return
         if self._applied is None:
@@ -129,8 +180,24 @@ class FusedAdamWEMA:
         with torch.cuda.stream(self._side):
             for fn in after or ():
                 fn()
-            for lo, hi in self.layout.buckets[key]:
-                self._update(arena.flat, lo, hi)
+            if plan is None:
+                for lo, hi in self.layout.buckets[key]:
+                    self._update(arena.flat, lo, hi)
+            else:
+                dp = self._dp
+                for kind, lo, hi, grads in plan:
+                    if kind == "full":
+                        self._update(arena.flat, lo, hi)
+                    else:
+                        plo, phi = dp.part(lo, hi)
+                        self._update(grads, plo, phi, offset=plo)
+                        if self.shadow is not None:  # every rank's forward needs the whole region's bf16 weights
+                            w = dp.gather_region(self.shadow, lo, hi, async_op=True)
+                        else:
+                            w = dp.gather_region(self.flat, lo, hi, async_op=True)
+                        if w is not None:
+                            self._ag_pending.append(w)
+                self._stale = True
         self._applied.add(key)
 
     @torch.no_grad()
@@ -181,6 +248,7 @@ class FusedAdamWEMA:
         """state_dict of the EMA model (what train.py:233 saves under "ema"; download.py:26-29 loads it)."""
         if self.ema is None:
             raise L.Ditb200Error("this optimizer was built with ema_decay=None: there is no EMA model")
+        self._require_consolidated()
         ids = {id(p): self.layout.view(self.ema, p) for p in self.params}
         return {k: ids.get(id(v), v).detach().clone() for k, v in self.model.state_dict(keep_vars=True).items()}
 
@@ -202,6 +270,7 @@ class FusedAdamWEMA:
         "exp_avg_sq"}}, "param_groups": [...]} with i = position in model.parameters(), the numbering torch's
         AdamW(model.parameters()) uses (train.py:161, saved as "opt" at train.py:234; the frozen pos_embed takes a
         number but has no state) — plus the EMA weights under "ema" (per-parameter, cloned).  Every tensor is a copy."""
+        self._require_consolidated()
         m, v = self._named_views(self.exp_avg), self._named_views(self.exp_avg_sq)
         names = [k for k, p in self.model.named_parameters()]
         step = torch.tensor(float(self.step_count))

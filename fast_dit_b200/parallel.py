@@ -110,15 +110,30 @@ class DataParallel(torch.nn.Module):
     all-reduced (mean) asynchronously, so NCCL traffic over NVLink overlaps the rest of backward.  The
     compute stream waits for all collectives only at the end of backward."""
 
-    def __init__(self, module, process_group=None, broadcast_parameters: bool = True, grad_dtype=torch.float32):
+    def __init__(self, module, process_group=None, broadcast_parameters: bool = True, grad_dtype=torch.float32,
+                 shard_optimizer: bool = False):
         """grad_dtype=torch.bfloat16 sends the buckets over NVLink as bf16 (half the bytes; the f32 arena is rounded
         once on the way out and refilled from the averaged bf16 values).  The default, f32, is what the reference's
-        DistributedDataParallel does."""
+        DistributedDataParallel does.
+
+        shard_optimizer=True (needs an optim.FusedAdamWEMA on the module; f32 wire): the optimizer state is
+        partitioned over the ranks.  Per bucket, the GEMM-weight regions (99.5 % of DiT-XL/2) are REDUCE-SCATTERED
+        instead of all-reduced — each rank receives the mean of 1/W of every region, half the NVLink traffic of an
+        all-reduce — the rank applies AdamW + EMA to that part only (the HBM-bound optimizer pass shrinks by W), and the
+        updated bf16 weight shadows, the only copy of those weights the forward reads, are ALL-GATHERED back, issued
+        bucket by bucket while backward is still running.  Biases, embedders, final linear and adaLN biases (0.5 %)
+        stay replicated: all-reduced and updated on every rank.  Same arithmetic as the replicated optimizer; the f32
+        master weights, Adam moments and EMA of a region live on its owner only until consolidate() gathers them
+        (state_dict / ema_state_dict do that)."""
         super().__init__()
         import torch.distributed as dist
 
         if grad_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("grad_dtype must be torch.float32 or torch.bfloat16")
+        if shard_optimizer and grad_dtype != torch.float32:
+            raise ValueError("shard_optimizer reduce-scatters f32 gradients; grad_dtype must be torch.float32")
+        self.shard_optimizer = bool(shard_optimizer)
+        self._grad_parts = {}  # (lo, hi) of a sharded region -> this rank's averaged gradient part
         self.grad_dtype = grad_dtype
         self.module = module
         self.pg = process_group
@@ -140,7 +155,28 @@ class DataParallel(torch.nn.Module):
             flat = getattr(module, "_flat", None)
             if flat is not None:
                 flat.resync_from_parameters()
+        self.rank = dist.get_rank(process_group) if dist.is_initialized() else 0
+        if self.shard_optimizer:
+            opt = getattr(module, "_flat", None)
+            if opt is None or not hasattr(opt, "enable_sharding"):
+                raise ValueError("shard_optimizer=True needs an optim.FusedAdamWEMA built on the module first")
+            opt.enable_sharding(self)
         module._grad_sync = self._sync
+
+    # ---------------------------------------------------------------- collectives of the sharded optimizer
+    def part(self, lo, hi):
+        """This rank's part [plo, phi) of the sharded region [lo, hi)."""
+        n = (hi - lo) // self.world
+        return lo + self.rank * n, lo + (self.rank + 1) * n
+
+    def gather_region(self, flat, lo, hi, async_op=False):
+        """All-gather: every rank contributes its part of flat[lo:hi] and receives the others'."""
+        import torch.distributed as dist
+
+        plo, phi = self.part(lo, hi)
+        if self.world == 1:
+            return None
+        return dist.all_gather_into_tensor(flat[lo:hi], flat[plo:phi].clone(), group=self.pg, async_op=async_op)
 
     def _sync(self, key, arena):
         import torch.distributed as dist
@@ -173,6 +209,26 @@ class DataParallel(torch.nn.Module):
 
             self._dynamic_prev = ops.set_gemm_dynamic(True)
         first = len(self._pending)
+        if self.shard_optimizer:
+            lay = arena.layout
+            plan, works = [], []
+            for lo, hi in lay.big[key]:  # reduce-scatter: this rank gets the mean of its part
+                plo, phi = self.part(lo, hi)
+                out = self._grad_parts.get((lo, hi))
+                if out is None:
+                    out = self._grad_parts[(lo, hi)] = torch.empty(phi - plo, device=arena.flat.device, dtype=torch.float32)
+                cuda = arena.flat.is_cuda
+                w = dist.reduce_scatter_tensor(out, arena.flat[lo:hi], op=dist.ReduceOp.AVG if cuda else dist.ReduceOp.SUM,
+                                               group=self.pg, async_op=True)
+                works.append((w, out, cuda))
+                plan.append(("shard", lo, hi, out))
+            for lo, hi in lay.small[key]:  # replicated tail: all-reduce, updated everywhere
+                buf = arena.flat[lo:hi]
+                cuda = buf.is_cuda
+                w = dist.all_reduce(buf, op=dist.ReduceOp.AVG if cuda else dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                works.append((w, buf, cuda))
+                plan.append(("full", lo, hi, buf))
+            return ([lambda w=w, b=b, a=a: finish(w, b, a) for (w, b, a) in works], plan)
         for buf in arena.bucket(key):
             if buf.is_cuda and self.grad_dtype == torch.bfloat16:
                 from . import ops

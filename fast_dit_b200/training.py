@@ -41,6 +41,7 @@ class ArenaLayout:
     'blocks.i' for i = L-1..0, 'embed' (which also carries the small adaLN-bias region)."""
 
     ALIGN = 64  # floats: gradients start on 256-byte boundaries (vector atomics, 128-bit stores)
+    SHARD_ALIGN = 512  # floats: a region an optimizer shard is cut from divides evenly among <= 8 ranks, 64-float parts
 
     def __init__(self, model):
         ada_w, ada_b = model._ada_params()
@@ -60,29 +61,46 @@ class ArenaLayout:
         self.offsets, self.ranges = {}, {}
         off = 0
 
-        def place(plist, pad):
+        def place(plist, pad, align=None):
             nonlocal off
+            align = align or self.ALIGN
             lo = off
             for p in plist:
                 self.offsets[id(p)] = (off, p.numel(), tuple(p.shape))
                 off += p.numel()
                 if pad:
                     off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-            off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            off = (off + align - 1) // align * align
             return lo, off
 
+        # Inside a block the four GEMM weights come first and the biases after them: the weight part (99.9 % of the
+        # block) is what a sharded optimizer reduce-scatters and updates 1/W of per rank (parallel.DataParallel
+        # (shard_optimizer=True)); the small tail is all-reduced and updated everywhere.
+        self.big, self.small = {}, {}
         for key in ["embed"] + [f"blocks.{i}" for i in range(model.depth)] + ["final_layer"]:
-            self.ranges[key] = place(groups[key], True)
+            if key.startswith("blocks."):
+                off = (off + self.SHARD_ALIGN - 1) // self.SHARD_ALIGN * self.SHARD_ALIGN
+                lo, mid = place([p for p in groups[key] if p.dim() >= 2], True, self.SHARD_ALIGN)
+                _, hi = place([p for p in groups[key] if p.dim() < 2], True)
+                self.ranges[key], self.big[key], self.small[key] = (lo, hi), [(lo, mid)], [(mid, hi)]
+            else:
+                self.ranges[key] = place(groups[key], True)
+                self.big[key], self.small[key] = [], [self.ranges[key]]
         assert all(p.numel() % 4 == 0 for p in ada_w + ada_b)
         self.ranges["ada_w"] = place([p for p in ada_w if p.requires_grad], False)
         self.ranges["ada_b"] = place([p for p in ada_b if p.requires_grad], False)
         self.total = off
         self.ada_rows = sum(p.shape[0] for p in ada_w)
         self.buckets = {"embed": [self.ranges["embed"], self.ranges["ada_b"]]}
+        self.small["embed"] = [self.ranges["embed"], self.ranges["ada_b"]]
         for i, p in enumerate(ada_w):
             key = f"blocks.{i}" if i < model.depth else "final_layer"
             o, n, _ = self.offsets[id(p)]
             self.buckets[key] = [self.ranges[key], (o, o + n)]
+            if n % self.SHARD_ALIGN == 0:
+                self.big[key] = self.big[key] + [(o, o + n)]
+            else:  # odd hidden sizes: the adaLN slice stays replicated
+                self.small[key] = self.small[key] + [(o, o + n)]
 
     def view(self, flat, p):
         off, n, shape = self.offsets[id(p)]
@@ -262,9 +280,12 @@ class _DiTFunction(torch.autograd.Function):
             overlap_backward=True; it runs after the bucket's collective)."""
             reduce = getattr(model, "_grad_sync", None)
             after = reduce(key, arena) if reduce is not None else None
+            plan = None
+            if isinstance(after, tuple):  # sharded optimizer: (what to wait for, which parts this rank updates)
+                after, plan = after
             ready = getattr(model, "_bucket_ready", None)
             if ready is not None:
-                ready(key, arena, after)
+                ready(key, arena, after, plan)
 
         w = sh["w"]
         ada_w = sh["ada_w"]

@@ -45,15 +45,17 @@ def _worker(rank, world, port, q):
         torch.cuda.set_device(local)
         dev = torch.device("cuda", local)
         res = {}
-        for wire, overlap in ((torch.float32, False), (torch.bfloat16, False), (torch.float32, True), (torch.bfloat16, True)):
+        after_step = {}
+        for wire, overlap in ((torch.float32, False), (torch.bfloat16, False), (torch.float32, True), (torch.bfloat16, True),
+                              (torch.float32, "shard")):
             torch.manual_seed(7 * world + rank)  # rank-dependent initial weights
             m = DiT_models["DiT-S/4"](input_size=32, num_classes=1000, precision="bf16")
             rerandomise_zero_params(m, seed=1234 + rank)
             m = m.to(dev).train()
-            opt = FusedAdamWEMA(m, lr=1e-3, weight_decay=0.0, ema_decay=0.99, overlap_backward=overlap)
+            opt = FusedAdamWEMA(m, lr=1e-3, weight_decay=0.0, ema_decay=0.99, overlap_backward=overlap is True)
             before = m.blocks[0].attn.qkv.weight.detach().clone()
-            net = DataParallel(m, grad_dtype=wire)
-            tag = ("f32" if wire == torch.float32 else "bf16") + ("+overlap" if overlap else "")
+            net = DataParallel(m, grad_dtype=wire, shard_optimizer=overlap == "shard")
+            tag = ("f32" if wire == torch.float32 else "bf16") + ("+shard" if overlap == "shard" else "+overlap" if overlap else "")
             # ---- replicas agree after construction
             flat = opt.flat.clone()
             ref = flat.clone()
@@ -89,6 +91,24 @@ def _worker(rank, world, port, q):
             # ---- one step: replicas stay identical
             opt.step()
             opt.zero_grad()
+            if overlap == "shard":
+                # the bf16 shadows (what the forward reads) are complete on every rank without consolidating ...
+                sh = opt.shadow.clone()
+                ref = sh.clone()
+                dist.broadcast(ref, src=0)
+                res[tag + ".shadow_equal_after_step"] = bool(torch.equal(sh, ref))
+                # ... the f32 state is not, and says so, until every rank consolidates
+                try:
+                    m.state_dict()
+                    res[tag + ".state_dict_guard"] = False
+                except Exception:
+                    res[tag + ".state_dict_guard"] = True
+                opt.consolidate()
+                m.state_dict()
+                res[tag + ".shadow_follows_weights"] = bool(torch.equal(opt.shadow, opt.flat.bfloat16()))
+                res[tag + ".vs_replicated"] = _rel(opt.flat, after_step["f32"])
+                res[tag + ".ema_vs_replicated"] = _rel(opt.ema, after_step["f32.ema"])
+            after_step[tag], after_step[tag + ".ema"] = opt.flat.clone(), opt.ema.clone()
             flat = opt.flat.clone()
             ref = flat.clone()
             dist.broadcast(ref, src=0)
@@ -149,7 +169,14 @@ def test_data_parallel_over_nccl_two_ranks():
         res = out[rank]
         assert "error" not in res, res.get("error")
         print(f"rank {rank}: " + ", ".join(f"{k}={v if isinstance(v, bool) else f'{v:.2e}'}" for k, v in res.items()))
-        for tag, tol in (("f32", 2e-3), ("bf16", 8e-3), ("f32+overlap", 2e-3), ("bf16+overlap", 8e-3)):
+        assert res["f32+shard.shadow_equal_after_step"] and res["f32+shard.state_dict_guard"], (rank, res)
+        assert res["f32+shard.shadow_follows_weights"], (rank, res)
+        # same update as the replicated optimizer (the gradients differ run to run by the atomics' rounding, ~1e-3
+        # relative, times lr = 1e-3 per step)
+        assert res["f32+shard.vs_replicated"] < 1e-4 and res["f32+shard.ema_vs_replicated"] < 1e-4, (rank, res)
+        for tag, tol in (("f32", 2e-3), ("bf16", 8e-3), ("f32+overlap", 2e-3), ("bf16+overlap", 8e-3), ("f32+shard", 2e-3)):
+            if tag.endswith("shard"):
+                continue  # its gradients live as parts on their owners: covered by the weight comparison above
             assert res[f"{tag}.updated_during_backward"] is tag.endswith("overlap"), (rank, tag)
             for k in ("weights_equal_rank0", "weights_changed_on_nonzero_rank", "shadow_matches", "ema_matches",
                       "weights_equal_after_step", "ema_equal_after_step"):

@@ -150,3 +150,95 @@ def test_two_rank_gloo_gradient_buckets():
         assert p.exitcode == 0
     same_weights, ok, order_ok = q.get(timeout=10)
     assert same_weights and ok and order_ok
+
+
+# ------------------------------------------------------------------ training: optimizer state sharded over the ranks
+class _FakeShardedOptimizer:
+    """Stands in for optim.FusedAdamWEMA on the CPU: 'update' = write -gradient into the weights it is told to
+    update, then hand the region back to the wrapper's all-gather."""
+
+    def __init__(self, model):
+        from fast_dit_b200.training import layout_for
+
+        self.model, self.layout = model, layout_for(model)
+        self.flat = torch.zeros(self.layout.total)
+        self.updated = torch.zeros(self.layout.total, dtype=torch.int32)
+        model._flat = self
+
+    def resync_from_parameters(self):
+        pass
+
+    def enable_sharding(self, dp):
+        self.dp = dp
+        self.model._bucket_ready = self._bucket_ready
+
+    def _bucket_ready(self, key, arena, after=None, plan=None):
+        if key is None:
+            return
+        for fn in after or ():
+            fn()
+        for kind, lo, hi, grads in plan:
+            if kind == "full":
+                self.flat[lo:hi] = -grads
+                self.updated[lo:hi] += 1
+            else:
+                plo, phi = self.dp.part(lo, hi)
+                assert grads.numel() == phi - plo
+                self.flat[plo:phi] = -grads
+                self.updated[plo:phi] += 1
+                self.dp.gather_region(self.flat, lo, hi)
+
+
+def _shard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from fast_dit_b200.models import DiT_models
+    from fast_dit_b200.parallel import DataParallel, init_from_env
+    from fast_dit_b200.training import GradArena
+
+    init_from_env("gloo")
+    torch.manual_seed(0)
+    m = DiT_models["DiT-S/8"](input_size=32)
+    opt = _FakeShardedOptimizer(m)
+    DataParallel(m, shard_optimizer=True)
+    lay = opt.layout
+    arena = GradArena(m)
+    # rank r's gradient of arena element i is (r + 1) * (1 + i mod 7): the mean over ranks is (W + 1) / 2 * (1 + i mod 7)
+    arena.flat.copy_((rank + 1.0) * (1.0 + torch.arange(lay.total) % 7))
+    order = ["final_layer"] + [f"blocks.{i}" for i in range(m.depth - 1, -1, -1)] + ["embed"]
+    for key in order:
+        after, plan = m._grad_sync(key, arena)  # what training._DiTFunction.backward's sync() does
+        m._bucket_ready(key, arena, after, plan)
+    m._grad_sync(None, arena)
+    want = -(world + 1) / 2.0 * (1.0 + torch.arange(lay.total) % 7)
+    covered = torch.zeros(lay.total, dtype=torch.bool)
+    for key in order:
+        for lo, hi in lay.buckets[key]:
+            covered[lo:hi] = True
+    ok_values = bool(torch.equal(opt.flat[covered], want[covered]))  # after the all-gathers every rank holds every update
+    # work split: a rank updated its part of every sharded region and all of every replicated one, nothing twice
+    mine = int(opt.updated.sum())
+    big = sum(hi - lo for k in order for lo, hi in lay.big[k])
+    small = sum(hi - lo for k in order for lo, hi in lay.small[k])
+    ok_split = int(opt.updated.max()) == 1 and mine == big // world + small
+    dist.barrier()
+    q.put((rank, ok_values, ok_split, big / (big + small)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_optimizer_collectives():
+    """DataParallel(shard_optimizer=True) over gloo: reduce-scatter of the weight regions, all-reduce of the small
+    replicated tail, this rank's parts handed to the optimizer, all-gather of what it updated."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, ok_values, ok_split, frac in res:
+        assert ok_values and ok_split, (rank, ok_values, ok_split)
+        assert frac > 0.9
