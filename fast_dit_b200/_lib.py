@@ -72,6 +72,7 @@ SIGNATURES = {
     "ditb200_last_error": (C.c_char_p, []),
     "ditb200_debug_tile_schedule": (_i, [_i] * 7 + [C.c_void_p, _i]),
     "ditb200_debug_gemm_plan": (_i, [_i] * 6 + [C.c_void_p]),
+    "ditb200_debug_gemm_table": (_i, [_i] * 4 + [C.c_void_p, _i, C.c_void_p]),
     "ditb200_debug_attention_path": (_i, [_i] * 3),
     "ditb200_sm_count": (_i, []),
     "ditb200_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

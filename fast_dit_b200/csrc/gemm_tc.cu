@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ditb200 {
@@ -55,6 +57,18 @@ struct EpiParams {
   int epilogue, out_bf16;
   int atomic;  // out += (f32 vector atomics): split-K partials and gradient accumulation
   int tma_store;  // bf16 output through smem staging + TMA store (tma_out is valid)
+};
+
+// Explicit tile schedule (kernel parameter, read through the constant bank): for every CTA pair the list of tiles it
+// processes, in order.  Used where mixing tile widths balances better than any uniform cover — N = 1152 on 74 pairs is
+// 5.19 rounds of 192-wide tiles, but 56 row panels cut 256|256|256|192|192 and 8 cut 6 x 192 pack into 42 pairs x
+// four 256-wide + 32 pairs x five 192-wide tiles with nothing left over (launch_cfg: plan_table).
+// entry = m_blk << 16 | (first column / 16) << 5 | (columns / 16)
+constexpr int kTabCap = 1024, kTabPairs = 160;
+struct SchedTable {
+  int use;
+  uint16_t start[kTabPairs + 1];
+  uint32_t e[kTabCap];
 };
 
 template <int kCG, int BN>
@@ -236,6 +250,9 @@ struct TileSched {
   int F, H, r, q;           // full tiles, narrow tiles, light-CTA threshold, narrow tiles per light CTA
   int split_k, n_tiles, num_units;
   int m_last;               // >= 0: tile rows are visited last-first (m_blk -> m_last - m_blk); -1: first-first
+  int col0;                 // first output column of the current tile (n_blk * bn, or the table's)
+  const uint32_t* tab;      // explicit schedule (SchedTable::e) or nullptr
+  int ti, tend;             // this pair's range of table entries
   int phase, cur, end_a;
   // dynamic mode (cluster launch control): the grid has one cluster per work unit; a running cluster finishes its
   // own unit and then cancels clusters that have not been launched yet and does their units.  SMs that become
@@ -250,6 +267,7 @@ struct TileSched {
     P = pairs, p = pair, split_k = split;
     const int m_tiles = (M + tile_m - 1) / tile_m;
     m_last = reverse_m ? m_tiles - 1 : -1;
+    col0 = 0, tab = nullptr, ti = tend = 0;
     n_tiles = (N + bn - 1) / bn;
     num_units = m_tiles * n_tiles * split_k;
     part_cols = part;
@@ -328,7 +346,18 @@ struct TileSched {
   // (still in L2) and finishes with the rows the next kernel, traversing the other way, reads first.
   template <int kCG>
   __host__ __device__ __forceinline__ bool next(int bn, int& m_blk, int& n_blk, int& ncols, int& split) {
-    const bool ok = next_unmirrored<kCG>(bn, m_blk, n_blk, ncols, split);
+    bool ok;
+    if (tab != nullptr) {
+      ok = ti < tend;
+      if (ok) {
+        const uint32_t e = tab[ti++];
+        m_blk = (int)(e >> 16), col0 = (int)((e >> 5) & 0x7ffu) << 4, ncols = (int)(e & 31u) << 4;
+        n_blk = col0 / bn, split = 0;
+      }
+    } else {
+      ok = next_unmirrored<kCG>(bn, m_blk, n_blk, ncols, split);
+      col0 = n_blk * bn;
+    }
     if (ok && m_last >= 0) m_blk = m_last - m_blk;
     return ok;
   }
@@ -491,7 +520,8 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_aux,
                const __grid_constant__ EpiParams ep, const int M, const int N, const int K, const int a_mn, const int b_mn,
-               const int split_k, const int part_cols, const int dyn, const int reverse_m) {
+               const int split_k, const int part_cols, const int dyn, const int reverse_m,
+               const __grid_constant__ SchedTable stab) {
   using Cfg = TcCfg<kCG, BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -553,6 +583,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int kb_per = (k_blocks + split_k - 1) / split_k;
   TileSched sched;
   sched.init(M, N, tile_m * kMC, BN, part_cols, split_k, (int)gridDim.x / (kCG * kMC), (int)blockIdx.x / (kCG * kMC), reverse_m);
+  if (kMC == 1 && stab.use) {
+    const int pr = (int)blockIdx.x / kCG;
+    sched.tab = stab.e, sched.ti = stab.start[pr], sched.tend = stab.start[pr + 1];
+  }
   if (kMC == 1 && dyn) {
     sched.dyn = 1, sched.role = (warp == 0) ? (leader ? 0 : 1) : 2;
     sched.clc_resp = smem_u32(clc_resp), sched.clc_full = clc_full, sched.clc_empty = clc_empty;
@@ -570,7 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t phase = 0;
     while (sched.next<kCG>(BN, m_blk, n_blk, ncols, split)) {
       const int row_a = (m_blk * kMC + (int)pair) * tile_m + (int)cta_rank * kBM;
-      const int row_b = n_blk * BN + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
+      const int row_b = sched.col0 + (int)cta_rank * (ncols / kCG);  // each CTA of a pair holds half of the tile's B rows
       const int kb0 = split * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1u);
@@ -674,7 +708,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // The residual tile does not depend on the MMAs: pull this warp's 32 x (ncols/2) block towards L2
         // while the accumulators are still being produced, so the epilogue loads below do not pay HBM latency.
         const int chunks_ = (ncols + 31) >> 5, c0_ = (chunks_ + 1) >> 1;
-        const int pc0 = n_blk * BN + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
+        const int pc0 = sched.col0 + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
         if (row0 + lane < M) {
           const float* rp = ep.resid + (size_t)(row0 + lane) * N + pc0;
           for (int c = 0; c < pn; ++c)
@@ -683,7 +717,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       if (ep.epilogue == DITB200_EPI_MUL_DGELU || ep.epilogue == DITB200_EPI_MUL_AUX) {  // same for the saved fc1 values (bf16: 64 columns per line)
         const int chunks_ = (ncols + 31) >> 5, c0_ = (chunks_ + 1) >> 1;
-        const int pc0 = n_blk * BN + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
+        const int pc0 = sched.col0 + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
         if (row0 + lane < M) {
           const __nv_bfloat16* up = ep.aux_in + (size_t)(row0 + lane) * N + pc0;
           for (int c = 0; c < pn; c += 2)
@@ -700,7 +734,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int col_off = half ? chunks0 * 32 : 0;  // first tile column of this warp
       const int nch = half ? chunks - chunks0 : chunks0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_off);
-      const int colw = n_blk * BN + col_off;
+      const int colw = sched.col0 + col_off;
       constexpr int NCH = BN / 64;
 #define EPI_CASE(E, O, A) epi_tile<E, O, A, NCH>(ep, taddr0, stg, lane, row0, colw, nch, M, N, add_bias)
       const bool has_aux = ep.aux_out != nullptr;
@@ -807,8 +841,131 @@ extern "C" int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int
   return (rows && n > cap) ? -n : n;
 }
 
+static void choose_tile_fwd(int M, int N, int K, int sms, int* cg_out, int* bn_out);  // choose_tile for a K-major weight
+
+// ------------------------------------------------------------------ explicit schedules (SchedTable)
+// Cost of one pair-tile of w columns, in column units: every tile streams the whole 256-row A panel, which costs
+// about as much as 104 further columns of MMA work (in-model, M = 16384, K = 4608: 192 columns 27.8 us, 256 columns
+// 33.8 us; profiles/r02_bench_c3_v1.json).
+static inline int tile_cost(int w) { return w + 104; }
+
+// Max load over the pairs of the formula schedule TileSched would run for width bn (host replay, same cost model).
+static int formula_load(int M, int N, int cg, int bn, int trans_w, int P) {
+  const int tile_m = kBM * cg;
+  const int part = narrow_cols(N, bn, cg, trans_w);
+  int mx = 0;
+  for (int p = 0; p < P; ++p) {
+    TileSched sc;
+    sc.init(M, N, tile_m, bn, part, 1, P, p);
+    int m_blk = 0, n_blk = 0, ncols = 0, split = 0, load = 0;
+    while (sc.next<1>(bn, m_blk, n_blk, ncols, split)) load += tile_cost(ncols);
+    mx = load > mx ? load : mx;
+  }
+  return mx;
+}
+
+// Two tile widths, two classes of pairs.  N = f * 256 + rem with (256 + rem) / 2 = wt a legal MMA width: a row panel is
+// cut either "mixed" — (f - 1) tiles of 256 and two of wt — or, where wt divides N, "uniform" into N / wt tiles of wt.
+// `a` panels are cut mixed; the 256-wide tiles go round-robin to the first nA pairs, the wt-wide ones to the others.
+// (a, nA) minimising the longest pair is found by enumeration; the table is used only if it beats the formula
+// schedule of the width the chooser would otherwise take by 3 %.  Returns the max load (0: no table).
+static int plan_table(int M, int N, int P, int formula, SchedTable* t) {
+  const int bn = 256, m_tiles = (M + 255) / 256, f = N / bn, rem = N % bn;
+  if (P > kTabPairs || P < 2 || rem == 0 || f < 1 || (bn + rem) % 32 != 0 || m_tiles > 65535 || N > 16 * 0x7ff) return 0;
+  const int wt = (bn + rem) / 2;
+  const bool uni = N % wt == 0;
+  const int cb = tile_cost(bn), cm = tile_cost(wt);
+  long best = -1;
+  int best_a = 0, best_na = 0;
+  for (int a = uni ? 0 : m_tiles; a <= m_tiles; ++a) {
+    const long B = (long)a * (f - 1), Mi = (long)a * 2 + (long)(m_tiles - a) * (uni ? N / wt : 0);
+    if (B + Mi > kTabCap) continue;
+    for (int nA = 0; nA <= P; ++nA) {
+      if ((nA == 0) != (B == 0) || (nA == P && Mi > 0)) continue;
+      const long la = nA ? (B + nA - 1) / nA * cb : 0, lb = Mi ? (Mi + (P - nA) - 1) / (P - nA) * cm : 0;
+      const long load = la > lb ? la : lb;
+      if (best < 0 || load < best) best = load, best_a = a, best_na = nA;
+    }
+  }
+  if (best < 0 || best * 100 > (long)formula * 97) return 0;
+  // build: big tiles in (panel, slot) order to pairs [0, nA) round-robin (concurrent pairs share A panels in L2);
+  // mid tiles likewise to pairs [nA, P)
+  const int a = best_a, nA = best_na, nB = P - nA;
+  auto entry = [](int m_blk, int col0, int w) { return ((uint32_t)m_blk << 16) | ((uint32_t)(col0 / 16) << 5) | (uint32_t)(w / 16); };
+  const long B = (long)a * (f - 1), Mi = (long)a * 2 + (long)(m_tiles - a) * (uni ? N / wt : 0);
+  int idx = 0;
+  for (int p = 0; p < P; ++p) {
+    t->start[p] = (uint16_t)idx;
+    if (p < nA) {
+      for (long i = p; i < B; i += nA) t->e[idx++] = entry((int)(i / (f - 1)), (int)(i % (f - 1)) * bn, bn);
+    } else {
+      for (long j = p - nA; j < Mi; j += nB) {
+        if (j < 2L * a) t->e[idx++] = entry((int)(j / 2), (f - 1) * bn + (int)(j % 2) * wt, wt);
+        else {
+          const long u = j - 2L * a;
+          const int per = N / wt;
+          t->e[idx++] = entry(a + (int)(u / per), (int)(u % per) * wt, wt);
+        }
+      }
+    }
+  }
+  t->start[P] = (uint16_t)idx;
+  for (int p = P + 1; p <= kTabPairs; ++p) t->start[p] = (uint16_t)idx;
+  t->use = 1;
+  return (int)best;
+}
+
+// Plans are cached per shape: the search runs once.
+struct TablePlan {
+  int M, N, P, load;
+  SchedTable tab;
+};
+static const SchedTable* table_for(int M, int N, int P, int formula) {
+  static std::mutex mu;
+  static TablePlan* plans[16];
+  static int n_plans = 0;
+  static const bool off = getenv("DITB200_GEMM_NO_TABLE") != nullptr;  // measurement switch
+  if (off) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  for (int i = 0; i < n_plans; ++i)
+    if (plans[i]->M == M && plans[i]->N == N && plans[i]->P == P) return plans[i]->load ? &plans[i]->tab : nullptr;
+  if (n_plans == 16) return nullptr;
+  TablePlan* pl = new TablePlan();
+  memset(pl, 0, sizeof(*pl));
+  pl->M = M, pl->N = N, pl->P = P;
+  pl->load = plan_table(M, N, P, formula, &pl->tab);
+  plans[n_plans++] = pl;
+  return pl->load ? &pl->tab : nullptr;
+}
+
+// Test hook (host only): the explicit schedule plan_table builds for an M x N forward GEMM on `pairs` CTA pairs, as rows
+// {pair, m_blk, first column, columns}; returns the number of rows, 0 when the formula schedule is kept, -needed when
+// cap is too small.  out_loads[2] = {formula max load, table max load} in tile_cost units.
+extern "C" int ditb200_debug_gemm_table(int M, int N, int K, int pairs, int* rows, int cap, int* out_loads) {
+  if (M <= 0 || N <= 0 || K <= 0 || pairs < 2 || pairs > kTabPairs) return 0;
+  int cg = 0, bn = 0;
+  choose_tile_fwd(M, N, K, pairs * 2, &cg, &bn);
+  if (cg != 2) return 0;
+  const int formula = formula_load(M, N, 2, bn, 0, pairs);
+  SchedTable* t = new SchedTable();
+  memset(t, 0, sizeof(*t));
+  const int load = plan_table(M, N, pairs, formula, t);
+  if (out_loads) out_loads[0] = formula, out_loads[1] = load;
+  int n = 0;
+  if (load) {
+    for (int p = 0; p < pairs; ++p)
+      for (int i = t->start[p]; i < t->start[p + 1]; ++i, ++n)
+        if (rows && n < cap) {
+          const uint32_t e = t->e[i];
+          rows[4 * n] = p, rows[4 * n + 1] = (int)(e >> 16), rows[4 * n + 2] = (int)((e >> 5) & 0x7ffu) * 16, rows[4 * n + 3] = (int)(e & 31u) * 16;
+        }
+  }
+  delete t;
+  return (rows && n > cap) ? -n : n;
+}
+
 template <int kCG, int BN, int kMC = 1>
-static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) {
+static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st, const SchedTable* table = nullptr) {
   using Cfg = TcCfg<kCG, BN>;
   CUtensorMap ta, tb;
   int rc;
@@ -894,9 +1051,12 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st) 
   const int dyn = (kMC == 1 && a->dynamic_sched && units > clusters) ? 1 : 0;
   const int part = kMC > 1 ? 0 : narrow_cols(a->N, BN, kCG, a->trans_w);
   if (dyn) clusters = units;  // one cluster per unit; the running ones cancel and absorb the rest
+  static const SchedTable no_table = {};
+  if (table != nullptr && (dyn || kMC > 1 || split_k > 1 || clusters != num_sms() / kCG)) table = nullptr;
   cfg.gridDim = dim3((unsigned)(clusters * kCG * kMC));
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<kCG, BN, kMC>, ta, tb, tout, taux, ep, a->M, a->N, a->K,
-                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part, dyn, a->reverse_m ? 1 : 0);
+                                     a->trans_a ? 1 : 0, a->trans_w ? 1 : 0, split_k, part, dyn, a->reverse_m ? 1 : 0,
+                                     table ? *table : no_table);
   if (e != cudaSuccess) return check_cuda(e, "gemm_tc launch");
   return 0;
 }
@@ -954,6 +1114,8 @@ static void choose_tile(int M, int N, int K, int trans_w, int split_k, int sms, 
   *bn_out = best_bn;
 }
 
+static void choose_tile_fwd(int M, int N, int K, int sms, int* cg_out, int* bn_out) { choose_tile(M, N, K, 0, 1, sms, cg_out, bn_out); }
+
 // Test hook: the tile shape the automatic chooser picks for a GEMM on a GPU with `sms` SMs: out = {cta_group,
 // tile_n, narrow last column}.  Host arithmetic only.
 extern "C" int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out) {
@@ -1002,6 +1164,12 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
     choose_tile(a->M, a->N, a->K, a->trans_w, split_k, num_sms(), &acg, &abn);
     if (cg == 0) cg = acg;
     if (bn == 0) bn = abn;
+  }
+  // Explicit two-width schedule where it beats every uniform cover (forward GEMMs with a K-major weight)
+  if (a->cta_group == 0 && a->tile_n == 0 && cg == 2 && !a->trans_w && split_k == 1 && !a->accumulate && !a->dynamic_sched) {
+    const int P = num_sms() / 2;
+    const SchedTable* tab = table_for(a->M, a->N, P, formula_load(a->M, a->N, 2, bn, 0, P));
+    if (tab != nullptr) return launch_cfg<2, 256>(a, split_k, st, tab);
   }
   static const bool mc_auto = getenv("DITB200_GEMM_MC") != nullptr;  // measurement switch: multicast clusters where they fit exactly
   if (mc_auto && a->cta_group == 0 && cg == 2 && bn == 256 && !a->trans_w && a->N % 256 == 0 && a->M % 512 == 0) cg = 4;

@@ -81,6 +81,11 @@ int ditb200_debug_tile_schedule(int M, int N, int tile_m, int bn, int part_cols,
 /* Test hook (host only): the tile the automatic chooser picks for an M x N x K GEMM on a GPU with `sms` SMs:
  * out[3] = {cta_group, tile_n, width of the narrow last tile column (0: none)}. */
 int ditb200_debug_gemm_plan(int M, int N, int K, int trans_w, int split_k, int sms, int* out);
+/* Test hook (host only): the explicit two-width tile schedule the GEMM uses where it balances better than a uniform
+ * cover (N = 1152 on 74 CTA pairs: 256|256|256|192|192 panels).  rows[4 * cap] receives {pair, m_blk, first column,
+ * columns} per tile in execution order; out_loads[2] = {longest pair under the formula schedule, under the table}
+ * in cost units.  Returns the number of tiles, 0 when the formula schedule is kept, -needed when cap is too small. */
+int ditb200_debug_gemm_table(int M, int N, int K, int pairs, int* rows, int cap, int* out_loads);
 /* Test hook (host only): kernel family that serves bf16 attention for T tokens per image and head dim hd:
  * 2 = tcgen05, K/V streamed in 128-key blocks (forward, T = 512 / 768 / 1024 ...), 1 = tcgen05 whole-row kernels
  * (T = 128 / 256 forward, T = 256 backward), 0 = mma.sync flash kernels (every other T), -1 = unsupported head dim. */

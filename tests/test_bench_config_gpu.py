@@ -233,3 +233,28 @@ def test_zigzag_traversal_is_bit_identical(monkeypatch):
         monkeypatch.setattr(models, "_ZIGZAG", True)
         zig = m(xx.cuda(), t.cuda(), yy.cuda())
     assert torch.equal(base, zig)
+
+
+@pytest.mark.parametrize("N,K", [(1152, 4608), (1152, 1152)])
+def test_gemm_explicit_schedule_matches_uniform_tiles(dev, N, K):
+    """The two-width tile table (256|256|256|192|192 row panels, chosen automatically at M = 16384, N = 1152) against the
+    same GEMM forced onto uniform 192-wide and 128-wide tiles: same k order per output element, so bit-identical."""
+    from fast_dit_b200 import _lib as L
+    from fast_dit_b200 import ops
+
+    M, T = 16384, 256
+    g = torch.Generator(device=dev).manual_seed(91)
+    a = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    auto = ops.gemm(a, w, bias)
+    assert torch.equal(auto, ops.gemm(a, w, bias, tile_n=192, cta_group=2))
+    assert torch.equal(auto, ops.gemm(a, w, bias, tile_n=128, cta_group=2))
+    assert torch.equal(auto, ops.gemm(a, w, bias, reverse_m=True))
+    assert rel_l2(auto.float(), _ref_mm(a, w, bias)) < 4e-3
+    resid = torch.randn(M, N, device=dev, generator=g)
+    gate = torch.randn(M // T, N, device=dev, generator=g)
+    x1, x2 = resid.clone(), resid.clone()
+    ops.gemm(a, w, bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x1, gate=gate, rows_per_gate=T)
+    ops.gemm(a, w, bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=x2, gate=gate, rows_per_gate=T, tile_n=192, cta_group=2)
+    assert torch.equal(x1, x2)
