@@ -868,7 +868,7 @@ static int formula_load(int M, int N, int cg, int bn, int trans_w, int P) {
 // cut either "mixed" — (f - 1) tiles of 256 and two of wt — or, where wt divides N, "uniform" into N / wt tiles of wt.
 // `a` panels are cut mixed; the 256-wide tiles go round-robin to the first nA pairs, the wt-wide ones to the others.
 // (a, nA) minimising the longest pair is found by enumeration; the table is used only if it beats the formula
-// schedule of the width the chooser would otherwise take by 3 %.  Returns the max load (0: no table).
+// schedule of the width the chooser would otherwise take by 2 %.  Returns the max load (0: no table).
 static int plan_table(int M, int N, int P, int formula, SchedTable* t) {
   const int bn = 256, m_tiles = (M + 255) / 256, f = N / bn, rem = N % bn;
   if (P > kTabPairs || P < 2 || rem == 0 || f < 1 || (bn + rem) % 32 != 0 || m_tiles > 65535 || N > 16 * 0x7ff) return 0;
@@ -887,7 +887,7 @@ static int plan_table(int M, int N, int P, int formula, SchedTable* t) {
       if (best < 0 || load < best) best = load, best_a = a, best_na = nA;
     }
   }
-  if (best < 0 || best * 100 > (long)formula * 97) return 0;
+  if (best < 0 || best * 100 > (long)formula * 98) return 0;
   // build: big tiles in (panel, slot) order to pairs [0, nA) round-robin (concurrent pairs share A panels in L2);
   // mid tiles likewise to pairs [nA, P)
   const int a = best_a, nA = best_na, nB = P - nA;

@@ -207,13 +207,13 @@ def test_bench_reference_arm_prints_the_contract_line():
 
 
 @pytest.mark.parametrize("M,N,K,expect_table", [(16384, 1152, 4608, True), (16384, 1152, 1152, True), (8192, 3456, 1152, True),
-                                                (16384, 4608, 1152, False), (16384, 3456, 1152, False), (1024, 1152, 1152, False),
+                                                (16384, 4608, 1152, False), (16384, 3456, 1152, True), (1024, 1152, 1152, False),
                                                 (16384, 1160, 1152, False)])
 def test_gemm_explicit_two_width_schedule(M, N, K, expect_table):
     """Where mixing 256-wide and (256 + N mod 256) / 2-wide tiles balances better than any uniform cover, the GEMM runs an
     explicit per-pair tile list (N = 1152 on 74 pairs: 42 pairs x four 256-wide + 32 pairs x five 192-wide tiles instead
     of six rounds of 192).  Host replay: every output element is covered exactly once, widths are legal MMA widths, and
-    the longest pair is at least 3 % shorter than under the formula schedule."""
+    the longest pair is at least 2 % shorter than under the formula schedule."""
     import ctypes
     from fast_dit_b200 import _lib as L
 
@@ -233,6 +233,6 @@ def test_gemm_explicit_two_width_schedule(M, N, K, expect_table):
         cover[m, c0 // 16:(c0 + w) // 16] += 1
     assert (cover == 1).all()
     per_pair = np.bincount(rows[:, 0], weights=rows[:, 3] + 104, minlength=74)
-    assert per_pair.max() == loads[1] and loads[1] * 100 <= loads[0] * 97
+    assert per_pair.max() == loads[1] and loads[1] * 100 <= loads[0] * 98
     if (M, N) == (16384, 1152):
         assert n == 56 * 5 + 8 * 6 and sorted(set(per_pair.tolist())) == [4 * 360.0, 5 * 296.0]
