@@ -30,6 +30,7 @@ from . import ops
 PRECISIONS = ("bf16", "fp32")
 _BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "2"))
 _ZIGZAG = os.environ.get("DITB200_ZIGZAG", "1") != "0"
+_EXP_DEFER = os.environ.get("DITB200_EXP_DEFER") is not None  # TIMING EXPERIMENT ONLY (wrong results): see DESIGN §8
 
 
 # --------------------------------------------------------------- parameter holders
@@ -308,7 +309,8 @@ class DiT(nn.Module):
             o = ops.attention(qkv, N, T, Hh, hd, reverse=nxt())
             if branch:
                 yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, reverse_m=nxt())
-                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok, reverse=nxt())
+                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok, reverse=nxt(),
+                                             write_x=not _EXP_DEFER)
             else:
                 ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g1,
                          rows_per_gate=T, reverse_m=nxt())

@@ -166,8 +166,9 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
 
 
 def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None,
-                      x_out=None, want_out: bool = True, reverse: bool = False):
-    """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out)."""
+                      x_out=None, want_out: bool = True, reverse: bool = False, write_x: bool = True):
+    """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out).
+    write_x=False: the updated stream is not written back (a later kernel applies the same update); returns (None, out)."""
     lib = _lib_for(x)
     M, D = x.shape
     B = M // T
@@ -176,7 +177,10 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
     assert gate.stride(1) == 1
     if want_out:
         assert shift.stride(1) == 1 and scale.stride(1) == 1 and gate.stride(0) == shift.stride(0) == scale.stride(0)
-    if x_out is None:
+    if not write_x:
+        assert want_out
+        x_out = None
+    elif x_out is None:
         x_out = torch.empty_like(x)
     out = torch.empty((M, D), device=x.device, dtype=out_dtype) if want_out else None
     _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift if want_out else None),

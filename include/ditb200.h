@@ -145,7 +145,9 @@ int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, 
 /* Gated residual update fused in front of ditb200_ln_modulate (the training forward keeps the branch output y
  * for backward, so the GEMM that produces it needs no residual traffic of its own):
  *   x_out[b,t,:] = x[b,t,:] + gate[b,:] * y[b,t,:]                      (models_original.py:120-121)
- *   out[b,t,:]   = LN(x_out[b,t,:]) * (1 + scale[b,:]) + shift[b,:]     (out == NULL: only x_out)
+ *   out[b,t,:]   = LN(x_out[b,t,:]) * (1 + scale[b,:]) + shift[b,:]     (out == NULL: only x_out;
+ *                                                                         x_out == NULL: only out — the update of
+ *                                                                         the stream is left to a later kernel)
  * x, x_out f32 [B*T, D] (may alias); y bf16 [B*T, D]; gate/shift/scale [B, D] slices with row stride mod_stride;
  * out bf16 or f32; stats as in ditb200_ln_modulate.  D must be 384, 768, 1024 or 1152. */
 int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
