@@ -193,7 +193,7 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
 def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
          rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0,
          aux_out=None, aux_in=None, accumulate: bool = False, split_k: int = 0, trans_a: bool = False,
-         trans_w: bool = False, reverse_m: bool = False):
+         trans_w: bool = False, reverse_m: bool = False, gate_aux=None):
     """out = epilogue(op(a) @ op(w).T).  a[M,K] (or [K,M] with trans_a), w[N,K] (or [K,N] with trans_w), both
     bf16 (tcgen05) or both f32 (check mode, forward only)."""
     lib = _lib_for(a)
@@ -208,6 +208,8 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
         if out is None:
             out = resid  # in place on the residual stream
         assert gate is not None and gate.stride(1) == 1
+        if gate_aux is not None:  # a deferred earlier branch rides along: out = resid + gate_aux * aux_in + gate * (acc + bias)
+            assert aux_in is not None and gate_aux.stride(1) == 1 and gate_aux.stride(0) == gate.stride(0)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
     assert out.shape == (M, N) and out.is_contiguous()
@@ -216,7 +218,7 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
                       _DT[out.dtype], engine, tile_n, cta_group,
                       _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
-                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC), int(reverse_m))
+                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC), _p(gate_aux), int(reverse_m))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
           meta=2.0 * M * N * K,
           tag=None if _PROFILE is None else

@@ -228,6 +228,12 @@ typedef struct ditb200_gemm_args {
                           clusters cancel and absorb the ones not yet launched, so SMs held by another kernel (the
                           overlapped NCCL all-reduce of a data-parallel backward, the role of torch DDP in
                           train_options/train_original.py:149) never own tiles.  Same results bit for bit. */
+  const float* gate_aux; /* TCGEN05, EPI_BIAS_GATE_RESID: a second branch whose update was deferred rides along,
+                            out = resid + gate_aux[b,:] * aux_in + gate[b,:] * (acc + bias), with aux_in [M, N] bf16 and
+                            gate_aux laid out like gate (same gate_stride).  The inference path uses it for fc2: LayerNorm 2
+                            normalises x + gate_msa * proj(...) without writing it back (ditb200_ln_modulate_resid,
+                            x_out = NULL) and fc2's epilogue, which reads and rewrites the stream anyway, applies both
+                            updates of the block (models_original.py:120-121).  NULL = off. */
   int reverse_m;       /* TCGEN05: visit the tile rows last-first.  Kernels of a chain alternate their direction so
                           that each starts on the rows its producer wrote last (still in the 126 MB L2).  Same
                           results bit for bit. */
