@@ -32,7 +32,7 @@ class GemmArgs(C.Structure):
         ("M", _i), ("N", _i), ("K", _i),
         ("epilogue", _i), ("out_dtype", _i), ("engine", _i), ("tile_n", _i), ("cta_group", _i),
         ("aux_out", _vp), ("aux_in", _vp), ("aux_dtype", _i), ("accumulate", _i), ("split_k", _i),
-        ("trans_a", _i), ("trans_w", _i), ("dynamic_sched", _i), ("gate_aux", _vp), ("reverse_m", _i),
+        ("trans_a", _i), ("trans_w", _i), ("dynamic_sched", _i), ("reverse_m", _i),
     ]
 
 

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
     const float2 y1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yv[j].y));
     v[j].x = fmaf(g4.x, y0.x, v[j].x), v[j].y = fmaf(g4.y, y0.y, v[j].y);
     v[j].z = fmaf(g4.z, y1.x, v[j].z), v[j].w = fmaf(g4.w, y1.y, v[j].w);
-    if (x_out != nullptr) reinterpret_cast<float4*>(x_out + (size_t)row * D)[lane + 32 * j] = v[j];
+    reinterpret_cast<float4*>(x_out + (size_t)row * D)[lane + 32 * j] = v[j];
     s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   }
   if (out == nullptr) return;
@@ -588,11 +588,11 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
 extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
                                          const float* scale, int mod_stride, float* x_out, void* out, int out_dtype,
                                          float* stats, int B, int T, int D, float eps, int reverse, void* stream) {
-  DITB_REQUIRE(x && y && gate && (x_out || out), DITB200_EINVAL, "ln_modulate_resid: null pointer");
+  DITB_REQUIRE(x && y && gate && x_out, DITB200_EINVAL, "ln_modulate_resid: null pointer");
   DITB_REQUIRE(out == nullptr || (shift && scale), DITB200_EINVAL, "ln_modulate_resid: out needs shift and scale");
   DITB_REQUIRE(B > 0 && T > 0 && (D == 384 || D == 768 || D == 1024 || D == 1152), DITB200_EINVAL,
                "ln_modulate_resid: bad shape B=%d T=%d D=%d (D in 384, 768, 1024, 1152)", B, T, D);
-  DITB_REQUIRE(mod_stride % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(gate) && (!x_out || aligned16(x_out)) &&
+  DITB_REQUIRE(mod_stride % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(gate) && aligned16(x_out) &&
                    (!out || (aligned16(out) && aligned16(shift) && aligned16(scale))),
                DITB200_EALIGN, "ln_modulate_resid: misaligned pointer or stride");
   DITB_REQUIRE(out_dtype == DITB200_F32 || out_dtype == DITB200_BF16, DITB200_EINVAL, "ln_modulate_resid: bad out_dtype");

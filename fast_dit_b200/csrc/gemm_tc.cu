@@ -51,7 +51,6 @@ struct EpiParams {
   void* out;
   const float* resid;
   const float* gate;
-  const float* gate_aux;  // GATE_RESID with a second, already computed branch: out = resid + gate_aux * aux_in + gate * (acc + bias)
   __nv_bfloat16* aux_out;
   const __nv_bfloat16* aux_in;
   int gate_stride, rows_per_gate;
@@ -123,22 +122,19 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
                                          const bool add_bias) {
   const int epi = EPI >= 0 ? EPI : ep.epilogue;
   const int omode = OUT >= 0 ? OUT : (ep.out_bf16 ? OUT_BF16 : (ep.atomic ? OUT_ATOMIC : OUT_F32));
-  const bool aux = AUX >= 0 ? (AUX == 1) : (ep.aux_out != nullptr);
-  const bool two = AUX >= 0 ? (AUX == 2) : (ep.gate_aux != nullptr);  // second branch rides along (GATE_RESID only)
+  const bool aux = AUX >= 0 ? (AUX != 0) : (ep.aux_out != nullptr);
   const int sub = lane >> 3, grp = lane & 7;
   const int rows_valid = M - row0;  // rows [0, rows_valid) of this warp's 32 exist (may be <= 0 or >= 32)
   const uint32_t my_row = stg + (uint32_t)lane * 128u;  // shared-window addresses
   const int swz_w = lane & 7;
   // adaLN gate: one [N] vector per image.  Fast path: all 32 rows belong to the same image.
   const float* gate_base = nullptr;
-  const float* gate2_base = nullptr;
   bool gate_uniform = true;
   if (epi == DITB200_EPI_BIAS_GATE_RESID) {
     const int last = min(row0 + 31, M - 1);
     const int g_lo = row0 / ep.rows_per_gate, g_hi = max(last, row0) / ep.rows_per_gate;
     gate_uniform = g_lo == g_hi;
     gate_base = ep.gate + (size_t)(rows_valid > 0 ? g_lo : 0) * ep.gate_stride;
-    if (two) gate2_base = ep.gate_aux + (size_t)(rows_valid > 0 ? g_lo : 0) * ep.gate_stride;
   }
   float4 r4[8];  // residual values of the chunk, requested before the accumulators are waited for (GATE_RESID only)
   uint2 u2[8];   // fc1 pre-activations of the chunk (MUL_DGELU only), same idea
@@ -157,7 +153,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
     uint32_t v[32];
     tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
     if (epi == DITB200_EPI_BIAS_GATE_RESID) load_resid(c, r4);
-    if (epi == DITB200_EPI_MUL_DGELU || epi == DITB200_EPI_MUL_AUX || (epi == DITB200_EPI_BIAS_GATE_RESID && two)) {
+    if (epi == DITB200_EPI_MUL_DGELU || epi == DITB200_EPI_MUL_AUX) {
       const int colp = colw + c * 32 + grp * 4;
       const __nv_bfloat16* up = ep.aux_in + (size_t)row0 * N + colp;
 #pragma unroll
@@ -175,9 +171,8 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
     if (col < N) {
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (add_bias) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (epi == DITB200_EPI_BIAS_GATE_RESID && gate_uniform) g4 = __ldg(reinterpret_cast<const float4*>(gate_base + col));
-      if (epi == DITB200_EPI_BIAS_GATE_RESID && two && gate_uniform) h4 = __ldg(reinterpret_cast<const float4*>(gate2_base + col));
       const size_t off0 = (size_t)row0 * N + col;
       float4 fr[8];  // all eight staged rows first: the shared loads overlap instead of one per row iteration
 #pragma unroll
@@ -216,15 +211,7 @@ __device__ __forceinline__ void epi_tile(const EpiParams& ep, const uint32_t tad
           } else if (epi == DITB200_EPI_BIAS_GATE_RESID) {
             if (!gate_uniform)
               g4 = __ldg(reinterpret_cast<const float4*>(ep.gate + (size_t)((row0 + r) / ep.rows_per_gate) * ep.gate_stride + col));
-            float4 rr = r4[i];
-            if (two) {  // the deferred update of the earlier branch first, in the order ln_modulate_resid applies it
-              if (!gate_uniform)
-                h4 = __ldg(reinterpret_cast<const float4*>(ep.gate_aux + (size_t)((row0 + r) / ep.rows_per_gate) * ep.gate_stride + col));
-              const uint2 pk = u2[i];
-              const float2 u0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.x));
-              const float2 u1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk.y));
-              rr.x = fmaf(h4.x, u0.x, rr.x), rr.y = fmaf(h4.y, u0.y, rr.y), rr.z = fmaf(h4.z, u1.x, rr.z), rr.w = fmaf(h4.w, u1.y, rr.w);
-            }
+            const float4 rr = r4[i];
             f.x = fmaf(g4.x, f.x, rr.x), f.y = fmaf(g4.y, f.y, rr.y), f.z = fmaf(g4.z, f.z, rr.z), f.w = fmaf(g4.w, f.w, rr.w);
           } else if (epi == DITB200_EPI_MUL_DGELU) {
             const uint2 pk = u2[i];
@@ -728,8 +715,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (pc0 + c * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + c * 32));
         }
       }
-      if (ep.epilogue == DITB200_EPI_MUL_DGELU || ep.epilogue == DITB200_EPI_MUL_AUX ||
-          (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID && ep.gate_aux != nullptr)) {  // same for the bf16 operand tile (64 columns per line)
+      if (ep.epilogue == DITB200_EPI_MUL_DGELU || ep.epilogue == DITB200_EPI_MUL_AUX) {  // same for the saved fc1 values (bf16: 64 columns per line)
         const int chunks_ = (ncols + 31) >> 5, c0_ = (chunks_ + 1) >> 1;
         const int pc0 = sched.col0 + (half ? c0_ * 32 : 0), pn = half ? chunks_ - c0_ : c0_;
         if (row0 + lane < M) {
@@ -768,9 +754,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       } else if (ep.epilogue == DITB200_EPI_BIAS_GELU && omode == OUT_BF16) {
         if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GELU, OUT_BF16, 1); else EPI_CASE(DITB200_EPI_BIAS_GELU, OUT_BF16, 0);
       } else if (ep.epilogue == DITB200_EPI_BIAS_GATE_RESID && omode == OUT_F32) {
-        if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 1);
-        else if (ep.gate_aux != nullptr) EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 2);
-        else EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 0);
+        if (has_aux) EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 1); else EPI_CASE(DITB200_EPI_BIAS_GATE_RESID, OUT_F32, 0);
       } else if (ep.epilogue == DITB200_EPI_MUL_DGELU && omode == OUT_BF16 && !has_aux) {
         EPI_CASE(DITB200_EPI_MUL_DGELU, OUT_BF16, 0);
       } else if (ep.epilogue == DITB200_EPI_MUL_AUX && omode == OUT_BF16 && !has_aux) {
@@ -993,7 +977,7 @@ static int launch_cfg(const ditb200_gemm_args* a, int split_k, cudaStream_t st, 
   else rc = make_tmap_2d(&tb, a->w, (uint64_t)a->K, (uint64_t)a->N, kBK, 64);
   if (rc) return rc;
   EpiParams ep;
-  ep.bias = a->bias, ep.out = a->out, ep.resid = a->resid, ep.gate = a->gate, ep.gate_aux = a->gate_aux;
+  ep.bias = a->bias, ep.out = a->out, ep.resid = a->resid, ep.gate = a->gate;
   ep.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
   ep.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
   ep.gate_stride = a->gate_stride, ep.rows_per_gate = a->rows_per_gate;
@@ -1158,10 +1142,6 @@ int launch_gemm_tcgen05(const ditb200_gemm_args* a, cudaStream_t st) {
   if (a->epilogue == DITB200_EPI_MUL_DGELU || a->epilogue == DITB200_EPI_MUL_AUX)
     DITB_REQUIRE(a->aux_in && aligned16(a->aux_in) && a->aux_dtype == DITB200_BF16, DITB200_EINVAL,
                  "gemm(tcgen05): MUL_DGELU / MUL_AUX need a 16-byte-aligned bf16 aux_in");
-  if (a->gate_aux)
-    DITB_REQUIRE(a->epilogue == DITB200_EPI_BIAS_GATE_RESID && a->aux_in && !a->aux_out && aligned16(a->aux_in) &&
-                     aligned16(a->gate_aux) && a->aux_dtype == DITB200_BF16, DITB200_EINVAL,
-                 "gemm(tcgen05): gate_aux goes with EPI_BIAS_GATE_RESID and a 16-byte-aligned bf16 aux_in (no aux_out)");
   if (a->epilogue == DITB200_EPI_BIAS_GELU_DAUX)
     DITB_REQUIRE(a->aux_out != nullptr, DITB200_EINVAL, "gemm(tcgen05): BIAS_GELU_DAUX needs aux_out");
   if (a->aux_out)

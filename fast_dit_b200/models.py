@@ -28,7 +28,7 @@ from . import _lib as L
 from . import ops
 
 PRECISIONS = ("bf16", "fp32")
-_BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "3"))
+_BRANCH_MODE = int(os.environ.get("DITB200_INFER_BRANCH", "2"))
 _ZIGZAG = os.environ.get("DITB200_ZIGZAG", "1") != "0"
 
 
@@ -284,9 +284,7 @@ class DiT(nn.Module):
         # Where the gated residual update `x + gate * branch` (MO:120-121) runs.  0: in the epilogue of the GEMM that
         # produces the branch (f32 stream read + written there).  1 / 2: the GEMM stores the bf16 branch by TMA and
         # the update rides in front of the next LayerNorm (ln_modulate_resid), for proj + fc2 / for proj only
-        # (proj's k loop is too short to hide the f32 epilogue).  3: as 2, but LayerNorm 2 does not write the updated
-        # stream back; fc2's epilogue, which reads and rewrites those rows anyway, applies both updates of the block
-        # (75 MB less HBM traffic per block; bit-identical to 2).  Chosen by measurement.
+        # (proj's k loop is too short to hide the f32 epilogue).  Chosen per build by measurement.
         branch = _BRANCH_MODE if (bf16 and D in (384, 768, 1024, 1152)) else 0  # widths ln_modulate_resid serves
         pend = None  # (branch output, gate) not yet folded into tok
         # Traversal direction: every kernel of the chain walks the token rows the opposite way to its producer, so it
@@ -308,11 +306,7 @@ class DiT(nn.Module):
                 pend = None
             qkv = ops.gemm(h, w[4 * i], blk.attn.qkv.bias, reverse_m=nxt())
             o = ops.attention(qkv, N, T, Hh, hd, reverse=nxt())
-            yb = None
-            if branch == 3:  # LayerNorm 2 sees x + g1 * proj but leaves the stream alone: fc2's epilogue applies both updates
-                yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, reverse_m=nxt())
-                _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, reverse=nxt(), write_x=False)
-            elif branch:
+            if branch:
                 yb = ops.gemm(o, w[4 * i + 1], blk.attn.proj.bias, reverse_m=nxt())
                 _, h = ops.ln_modulate_resid(tok, yb, g1, sh2, sc2, T, out_dtype=act, x_out=tok, reverse=nxt())
             else:
@@ -322,9 +316,6 @@ class DiT(nn.Module):
             u = ops.gemm(h, w[4 * i + 2], blk.mlp.fc1.bias, epilogue=L.EPI_BIAS_GELU, reverse_m=nxt())
             if branch == 1:
                 pend = (ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, reverse_m=nxt()), g2)
-            elif branch == 3:
-                ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g2,
-                         rows_per_gate=T, reverse_m=nxt(), aux_in=yb, gate_aux=g1)
             else:
                 ops.gemm(u, w[4 * i + 3], blk.mlp.fc2.bias, epilogue=L.EPI_BIAS_GATE_RESID, resid=tok, gate=g2,
                          rows_per_gate=T, reverse_m=nxt())

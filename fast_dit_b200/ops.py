@@ -166,9 +166,8 @@ def ln_modulate(x, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 
 
 
 def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16, eps: float = 1e-6, stats=None,
-                      x_out=None, want_out: bool = True, reverse: bool = False, write_x: bool = True):
-    """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out).
-    write_x=False: the updated stream is not written back (a later kernel applies the same update); returns (None, out)."""
+                      x_out=None, want_out: bool = True, reverse: bool = False):
+    """x_out = x + gate[b] * y (y bf16); out = LN(x_out) * (1 + scale[b]) + shift[b].  Returns (x_out, out)."""
     lib = _lib_for(x)
     M, D = x.shape
     B = M // T
@@ -177,10 +176,7 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
     assert gate.stride(1) == 1
     if want_out:
         assert shift.stride(1) == 1 and scale.stride(1) == 1 and gate.stride(0) == shift.stride(0) == scale.stride(0)
-    if not write_x:
-        assert want_out
-        x_out = None
-    elif x_out is None:
+    if x_out is None:
         x_out = torch.empty_like(x)
     out = torch.empty((M, D), device=x.device, dtype=out_dtype) if want_out else None
     _call("ln_modulate_resid", lib.ditb200_ln_modulate_resid, _p(x), _p(y), _p(gate), _p(shift if want_out else None),
@@ -193,7 +189,7 @@ def ln_modulate_resid(x, y, gate, shift, scale, T: int, out_dtype=torch.bfloat16
 def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resid=None, gate=None,
          rows_per_gate: int = 0, engine: Optional[int] = None, tile_n: int = 0, cta_group: int = 0,
          aux_out=None, aux_in=None, accumulate: bool = False, split_k: int = 0, trans_a: bool = False,
-         trans_w: bool = False, reverse_m: bool = False, gate_aux=None):
+         trans_w: bool = False, reverse_m: bool = False):
     """out = epilogue(op(a) @ op(w).T).  a[M,K] (or [K,M] with trans_a), w[N,K] (or [K,N] with trans_w), both
     bf16 (tcgen05) or both f32 (check mode, forward only)."""
     lib = _lib_for(a)
@@ -208,8 +204,6 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
         if out is None:
             out = resid  # in place on the residual stream
         assert gate is not None and gate.stride(1) == 1
-        if gate_aux is not None:  # a deferred earlier branch rides along: out = resid + gate_aux * aux_in + gate * (acc + bias)
-            assert aux_in is not None and gate_aux.stride(1) == 1 and gate_aux.stride(0) == gate.stride(0)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
     assert out.shape == (M, N) and out.is_contiguous()
@@ -218,7 +212,7 @@ def gemm(a, w, bias=None, *, epilogue=L.EPI_BIAS, out_dtype=None, out=None, resi
                       gate.stride(0) if gate is not None else 0, rows_per_gate, M, N, K, epilogue,
                       _DT[out.dtype], engine, tile_n, cta_group,
                       _p(aux_out), _p(aux_in), _DT[aux.dtype] if aux is not None else 0, int(accumulate), int(split_k),
-                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC), _p(gate_aux), int(reverse_m))
+                      int(trans_a), int(trans_w), int(_GEMM_DYNAMIC), int(reverse_m))
     _call("gemm_tc" if engine == L.GEMM_TCGEN05 else "gemm_fp32", lib.ditb200_gemm, C.byref(args), _stream(),
           meta=2.0 * M * N * K,
           tag=None if _PROFILE is None else

@@ -145,9 +145,7 @@ int ditb200_ln_modulate(const float* x, const float* shift, const float* scale, 
 /* Gated residual update fused in front of ditb200_ln_modulate (the training forward keeps the branch output y
  * for backward, so the GEMM that produces it needs no residual traffic of its own):
  *   x_out[b,t,:] = x[b,t,:] + gate[b,:] * y[b,t,:]                      (models_original.py:120-121)
- *   out[b,t,:]   = LN(x_out[b,t,:]) * (1 + scale[b,:]) + shift[b,:]     (out == NULL: only x_out;
- *                                                                         x_out == NULL: only out — the update of
- *                                                                         the stream is left to a later kernel)
+ *   out[b,t,:]   = LN(x_out[b,t,:]) * (1 + scale[b,:]) + shift[b,:]     (out == NULL: only x_out)
  * x, x_out f32 [B*T, D] (may alias); y bf16 [B*T, D]; gate/shift/scale [B, D] slices with row stride mod_stride;
  * out bf16 or f32; stats as in ditb200_ln_modulate.  D must be 384, 768, 1024 or 1152. */
 int ditb200_ln_modulate_resid(const float* x, const void* y, const float* gate, const float* shift,
@@ -228,12 +226,6 @@ typedef struct ditb200_gemm_args {
                           clusters cancel and absorb the ones not yet launched, so SMs held by another kernel (the
                           overlapped NCCL all-reduce of a data-parallel backward, the role of torch DDP in
                           train_options/train_original.py:149) never own tiles.  Same results bit for bit. */
-  const float* gate_aux; /* TCGEN05, EPI_BIAS_GATE_RESID: a second branch whose update was deferred rides along,
-                            out = resid + gate_aux[b,:] * aux_in + gate[b,:] * (acc + bias), with aux_in [M, N] bf16 and
-                            gate_aux laid out like gate (same gate_stride).  The inference path uses it for fc2: LayerNorm 2
-                            normalises x + gate_msa * proj(...) without writing it back (ditb200_ln_modulate_resid,
-                            x_out = NULL) and fc2's epilogue, which reads and rewrites the stream anyway, applies both
-                            updates of the block (models_original.py:120-121).  NULL = off. */
   int reverse_m;       /* TCGEN05: visit the tile rows last-first.  Kernels of a chain alternate their direction so
                           that each starts on the rows its producer wrote last (still in the 126 MB L2).  Same
                           results bit for bit. */
