@@ -82,8 +82,11 @@ SIGNATURES = {
     "ditb200_ln_modulate": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp]),
     "ditb200_ln_modulate_resid": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp]),
     "ditb200_ln_modulate_bwd": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ditb200_ln_modulate_bwd_gate": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i,
+                                          _vp, _i, _i, _i, _vp]),
     "ditb200_gate_resid_bwd": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp]),
     "ditb200_colsum": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "ditb200_adaln_wgrad": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_label_embed_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ditb200_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ditb200_unpatchify_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -22,6 +22,20 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
   *reinterpret_cast<uint2*>(p) = pk;
 }
 
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+// Asynchronous global -> shared copies (LDGSTS): in flight without holding registers, so ptxas cannot sink them.
+__device__ __forceinline__ void cp_async_16B(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8B(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ====================================================== LayerNorm + modulate, backward
 // h = xhat * (1 + scale[b]) + shift[b],  xhat = (x - mean) * rstd.
 //   dx      = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * (1 + scale[b])
@@ -163,6 +177,160 @@ __global__ void __launch_bounds__(128) ln_modulate_bwd_rows_kernel(
   }
 }
 
+// ============================ LayerNorm + modulate backward, fused with the NEXT gated-residual backward
+// In the backward chain every LayerNorm backward updates the gradient of the residual stream (dx), and the kernel
+// that follows it in data order is the gated-residual backward of the branch that joined the stream just before this
+// LayerNorm in the forward pass: dy = dx * gate[b], dgate[b] += sum_t dx * y, dbias += sum dy.  Run separately, that
+// kernel re-reads the dx this one has just written.  Here both happen in one pass over the rows.
+//
+// Mapping: a THREAD owns 4 consecutive columns of every row (CTA = D/4 threads = whole rows), so the four per-image
+// column sums (dshift, dscale, dgate, dbias) are 16 registers per thread however wide D is, and leave the CTA as
+// one 128-bit reduction each.  Rows go kFbRows at a time: all their loads are requested first (48 bytes per thread and
+// row in flight) — x and dh into registers, the operands of the second half (the previous dx and y) as asynchronous
+// copies into the thread's own shared-memory slots, because ptxas otherwise sinks those loads to their first use
+// behind the barrier and the batch pays three memory latencies instead of one.  The 2 * kFbRows row sums cross the
+// warp by a transposing shuffle reduction (9 shuffles, not 40) and the CTA through a double-buffered shared array
+// (one barrier per batch).  Persistent: each CTA takes one
+// contiguous range of row batches (at most a few images: the column sums are flushed when the image changes).
+constexpr int kFbRows = 4;
+template <int NT, typename TDh, bool kGate>
+__global__ void __launch_bounds__(NT, (NT <= 128 ? 4 : 2)) ln_modulate_bwd_cols_kernel(
+    const TDh* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ scale, int mod_stride,
+    const float* __restrict__ stats, float* __restrict__ dx, int accumulate, float* __restrict__ dshift,
+    float* __restrict__ dscale, int dmod_stride, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+    int gate_stride, __nv_bfloat16* __restrict__ dy, float* __restrict__ dgate, int dgate_stride,
+    float* __restrict__ dbias, int B, int T, int chunk) {
+  DITB_PDL_WAIT();
+  constexpr int D = NT * 4, NW = NT / 32;
+  __shared__ __align__(16) float red[2][NW][2 * kFbRows];
+  __shared__ __align__(16) float4 s_pv[kFbRows][NT];            // previous dx (accumulate != 0), slot [row][thread]
+  __shared__ __align__(8) uint2 s_y[kGate ? kFbRows : 1][NT];   // y (bf16 x 4)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid * 4;
+  const int bpi = T / kFbRows;  // row batches per image (T % kFbRows == 0: a batch never straddles two images)
+  const int nb = B * bpi;
+  const int q0 = blockIdx.x * chunk, q1 = min(nb, q0 + chunk);
+  if (q0 >= q1) return;
+  int b_cur = q0 / bpi;
+  float4 cv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b_cur * mod_stride + c));
+  float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (kGate) gv = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b_cur * gate_stride + c));
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 a_sh = zero4, a_sc = zero4, a_g = zero4, a_b = zero4;
+  auto flush = [&](int b) {
+    atomicAdd(reinterpret_cast<float4*>(dshift + (size_t)b * dmod_stride + c), a_sh);
+    atomicAdd(reinterpret_cast<float4*>(dscale + (size_t)b * dmod_stride + c), a_sc);
+    if constexpr (kGate) {
+      atomicAdd(reinterpret_cast<float4*>(dgate + (size_t)b * dgate_stride + c), a_g);
+      if (dbias != nullptr) atomicAdd(reinterpret_cast<float4*>(dbias + c), a_b);
+    }
+  };
+  int buf = 0;
+  for (int q = q0; q < q1; ++q, buf ^= 1) {
+    const int b = q / bpi;
+    if (b != b_cur) {
+      flush(b_cur);
+      a_sh = a_sc = a_g = a_b = zero4;
+      b_cur = b;
+      cv = __ldg(reinterpret_cast<const float4*>(scale + (size_t)b * mod_stride + c));
+      if constexpr (kGate) gv = __ldg(reinterpret_cast<const float4*>(gate + (size_t)b * gate_stride + c));
+    }
+    const size_t off0 = (size_t)q * kFbRows * D + c;  // row = q * kFbRows (bpi * kFbRows == T)
+    float4 xv[kFbRows], dv[kFbRows];
+    float2 st[kFbRows];
+#pragma unroll
+    for (int u = 0; u < kFbRows; ++u) {
+      const size_t off = off0 + (size_t)u * D;
+      if (accumulate) cp_async_16B(&s_pv[u][tid], dx + off);
+      if constexpr (kGate) cp_async_8B(&s_y[u][tid], y + off);
+    }
+#pragma unroll
+    for (int u = 0; u < kFbRows; ++u) {
+      const size_t off = off0 + (size_t)u * D;
+      xv[u] = ldg_stream_f4(reinterpret_cast<const float4*>(x + off));
+      dv[u] = load4(dh + off);
+      st[u] = __ldg(reinterpret_cast<const float2*>(stats) + (size_t)q * kFbRows + u);
+    }
+    float part[2 * kFbRows];
+#pragma unroll
+    for (int u = 0; u < kFbRows; ++u) {
+      const float mean = st[u].x, rstd = st[u].y;
+      // xv becomes xhat, the column sums take dh and dh * xhat, dv becomes g = dh * (1 + scale)
+      xv[u].x = (xv[u].x - mean) * rstd, xv[u].y = (xv[u].y - mean) * rstd;
+      xv[u].z = (xv[u].z - mean) * rstd, xv[u].w = (xv[u].w - mean) * rstd;
+      a_sh.x += dv[u].x, a_sh.y += dv[u].y, a_sh.z += dv[u].z, a_sh.w += dv[u].w;
+      a_sc.x += dv[u].x * xv[u].x, a_sc.y += dv[u].y * xv[u].y, a_sc.z += dv[u].z * xv[u].z, a_sc.w += dv[u].w * xv[u].w;
+      dv[u].x *= 1.f + cv.x, dv[u].y *= 1.f + cv.y, dv[u].z *= 1.f + cv.z, dv[u].w *= 1.f + cv.w;
+      part[u] = (dv[u].x + dv[u].y) + (dv[u].z + dv[u].w);
+      part[kFbRows + u] = (dv[u].x * xv[u].x + dv[u].y * xv[u].y) + (dv[u].z * xv[u].z + dv[u].w * xv[u].w);
+    }
+    // transposing warp reduction of the 8 partial sums: after the three exchange steps lane l holds value
+    // number (l >> 2) & 7 summed over the 8 lanes that share its low two bits; two plain steps finish it
+    static_assert(kFbRows == 4, "the shuffle network below reduces exactly 8 values");
+    float w4[4], w2[2], w1;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = hi ? part[i] : part[i + 4], keep = hi ? part[i + 4] : part[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = hi ? w4[i] : w4[i + 2], keep = hi ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+    }
+    {
+      const bool hi = lane & 4;
+      const float send = hi ? w2[0] : w2[1], keep = hi ? w2[1] : w2[0];
+      w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    // lane bits 4,3,2 = bits 2,1,0 of the value's number
+    if ((lane & 3) == 0) red[buf][warp][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = w1;
+    __syncthreads();
+    float4 t0 = zero4, t1 = zero4;  // row sums of g (rows 0..3) and of g * xhat
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float4 p0 = *reinterpret_cast<const float4*>(&red[buf][w][0]);
+      const float4 p1 = *reinterpret_cast<const float4*>(&red[buf][w][4]);
+      t0.x += p0.x, t0.y += p0.y, t0.z += p0.z, t0.w += p0.w;
+      t1.x += p1.x, t1.y += p1.y, t1.z += p1.z, t1.w += p1.w;
+    }
+    const float s1[kFbRows] = {t0.x * (1.0f / D), t0.y * (1.0f / D), t0.z * (1.0f / D), t0.w * (1.0f / D)};
+    const float s2[kFbRows] = {t1.x * (1.0f / D), t1.y * (1.0f / D), t1.z * (1.0f / D), t1.w * (1.0f / D)};
+    cp_async_wait_all();  // this thread's own slots: no barrier needed
+#pragma unroll
+    for (int u = 0; u < kFbRows; ++u) {
+      const size_t off = off0 + (size_t)u * D;
+      const float rstd = st[u].y;
+      float4 o;
+      o.x = rstd * (dv[u].x - s1[u] - xv[u].x * s2[u]), o.y = rstd * (dv[u].y - s1[u] - xv[u].y * s2[u]);
+      o.z = rstd * (dv[u].z - s1[u] - xv[u].z * s2[u]), o.w = rstd * (dv[u].w - s1[u] - xv[u].w * s2[u]);
+      if (accumulate) {
+        const float4 pv = s_pv[u][tid];
+        o.x += pv.x, o.y += pv.y, o.z += pv.z, o.w += pv.w;
+      }
+      *reinterpret_cast<float4*>(dx + off) = o;
+      if constexpr (kGate) {
+        const uint2 yv = s_y[u][tid];
+        const float4 yy = make_float4(__uint_as_float(yv.x << 16), __uint_as_float(yv.x & 0xffff0000u),
+                                      __uint_as_float(yv.y << 16), __uint_as_float(yv.y & 0xffff0000u));
+        const float4 d4 = make_float4(o.x * gv.x, o.y * gv.y, o.z * gv.z, o.w * gv.w);
+        store4(dy + off, d4);
+        a_g.x += o.x * yy.x, a_g.y += o.y * yy.y, a_g.z += o.z * yy.z, a_g.w += o.w * yy.w;
+        a_b.x += d4.x, a_b.y += d4.y, a_b.z += d4.z, a_b.w += d4.w;
+      }
+    }
+  }
+  flush(b_cur);
+}
+
 // ============================================================ gated residual, backward
 // x_out = x + gate[b] * y:  dy = dx_out * gate[b];  dgate[b] += sum_t dx_out * y;  dbias += sum_rows dy.
 // Thread = 4 columns, CTA = kGrRows tokens of one image: coalesced 128-bit row accesses, the
@@ -294,6 +462,70 @@ __global__ void __launch_bounds__(256) colsum4_kernel(const TIn* __restrict__ in
   atomicAdd(reinterpret_cast<float4*>(out + c), a);
 }
 
+// ===================================================== adaLN modulation Linear, weight + bias gradient
+// dW[r, c] = sum_b dmod[b, r] * sc[b, c],  dbias[r] = sum_b dmod[b, r]   (models_original.py:113-116 backward; b = image,
+// sc = silu(c) in bf16 as the forward GEMM read it).  The contraction runs over the BATCH only (32 images at C4), so
+// as a tensor-core GEMM it is one k block of mostly padding behind a 32 MB f32 store; here it is what it is: an
+// outer-product accumulation bound by that store.  CTA = 64 rows x 128 columns, thread = 8 rows x 4 columns, the two
+// operand tiles of 32 images at a time in shared memory (per image and thread: two broadcast 128-bit reads of
+// dmod, one of sc, 32 FMAs).  dmod is read in f32 straight from the buffer the backward kernels reduce into — no
+// bf16 copy — and the first column tile of every row tile also leaves the bias gradient.
+constexpr int kAwRows = 64, kAwCols = 128, kAwImgs = 32;
+__global__ void __launch_bounds__(256) adaln_wgrad_kernel(const float* __restrict__ dmod, int dmod_stride,
+                                                          const __nv_bfloat16* __restrict__ sc, float* __restrict__ dw,
+                                                          float* __restrict__ dbias, int N, int R, int D) {
+  DITB_PDL_WAIT();
+  __shared__ __align__(16) float s_d[kAwImgs][kAwRows];
+  __shared__ __align__(16) uint2 s_s[kAwImgs][kAwCols / 4];  // bf16 x 4 per entry
+  const int tid = threadIdx.x, tr = tid >> 5, tc = tid & 31;
+  const int r0 = blockIdx.x * kAwRows, c0 = blockIdx.y * kAwCols;
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float bsum = 0.f;
+  for (int b0 = 0; b0 < N; b0 += kAwImgs) {
+    const int nb = min(kAwImgs, N - b0);
+    if (b0 > 0) __syncthreads();
+    // both operand tiles as asynchronous copies (2 x 16 + 4 x 8 bytes per thread, all in flight at once; register
+    // loads get serialised load -> store -> load by ptxas); images past nb are zero rows
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {  // dmod: 16 float4 per image
+      const int i = tid + 256 * k, b = i >> 4, j = i & 15;
+      if (b < nb) cp_async_16B(&s_d[b][4 * j], dmod + (size_t)(b0 + b) * dmod_stride + r0 + 4 * j);
+      else *reinterpret_cast<float4*>(&s_d[b][4 * j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // sc: 32 groups of 4 bf16 per image
+      const int i = tid + 256 * k, b = i >> 5, j = i & 31;
+      if (b < nb) cp_async_8B(&s_s[b][j], sc + (size_t)(b0 + b) * D + c0 + 4 * j);
+      else s_s[b][j] = make_uint2(0u, 0u);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+#pragma unroll 4
+    for (int b = 0; b < kAwImgs; ++b) {  // images past nb are zero rows
+      const float4 d0 = *reinterpret_cast<const float4*>(&s_d[b][tr * 8]);
+      const float4 d1 = *reinterpret_cast<const float4*>(&s_d[b][tr * 8 + 4]);
+      const uint2 sr = s_s[b][tc];
+      const float4 s4 = make_float4(__uint_as_float(sr.x << 16), __uint_as_float(sr.x & 0xffff0000u),
+                                    __uint_as_float(sr.y << 16), __uint_as_float(sr.y & 0xffff0000u));
+      const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i].x = fmaf(d[i], s4.x, acc[i].x), acc[i].y = fmaf(d[i], s4.y, acc[i].y);
+        acc[i].z = fmaf(d[i], s4.z, acc[i].z), acc[i].w = fmaf(d[i], s4.w, acc[i].w);
+      }
+    }
+    if (blockIdx.y == 0 && tid < kAwRows) {
+      for (int b = 0; b < nb; ++b) bsum += s_d[b][tid];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(dw + (size_t)(r0 + tr * 8 + i) * D + c0 + tc * 4) = acc[i];
+  if (dbias != nullptr && blockIdx.y == 0 && tid < kAwRows) dbias[r0 + tid] = bsum;
+}
+
 // ================================================================ label embed, backward
 __global__ void label_embed_bwd_kernel(const float* __restrict__ dc, const int64_t* __restrict__ y,
                                        float* __restrict__ dtable, int B, int D, int num_rows) {
@@ -403,6 +635,69 @@ extern "C" int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float
   return 0;
 }
 
+// Fused entry: LayerNorm+modulate backward, then (y != NULL) the gated-residual backward of the branch that joined
+// the stream in front of this LayerNorm, on the dx just formed.  See ln_modulate_bwd_cols_kernel.
+template <int NT, typename TDh, bool kGate>
+static int launch_ln_bwd_cols(const void* dh, const float* x, const float* scale, int mod_stride, const float* stats,
+                              float* dx, int accumulate, float* dshift, float* dscale, int dmod_stride, const void* y,
+                              const float* gate, int gate_stride, void* dy, float* dgate, int dgate_stride,
+                              float* dbias, int B, int T, cudaStream_t st) {
+  static int per_sm = 0;  // resident CTAs per SM of this instantiation (a pure function of the kernel: racing writers agree)
+  if (per_sm == 0) {
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ln_modulate_bwd_cols_kernel<NT, TDh, kGate>, NT, 0);
+    if (e != cudaSuccess) return check_cuda(e, "ln_modulate_bwd_gate occupancy");
+    per_sm = n > 0 ? n : 1;
+  }
+  const int nb = B * (T / kFbRows);
+  int grid = num_sms() * per_sm;
+  if (grid > nb) grid = nb;
+  const int chunk = (nb + grid - 1) / grid;
+  grid = (nb + chunk - 1) / chunk;
+  DITB_KLAUNCH((ln_modulate_bwd_cols_kernel<NT, TDh, kGate>), dim3(grid), dim3(NT), 0, st,
+               reinterpret_cast<const TDh*>(dh), x, scale, mod_stride, stats, dx, accumulate, dshift, dscale, dmod_stride,
+               reinterpret_cast<const __nv_bfloat16*>(y), gate, gate_stride, reinterpret_cast<__nv_bfloat16*>(dy), dgate,
+               dgate_stride, dbias, B, T, chunk);
+  DITB_LAUNCH_CHECK("ln_modulate_bwd_gate");
+  return 0;
+}
+
+extern "C" int ditb200_ln_modulate_bwd_gate(const void* dh, int dh_dtype, const float* x, const float* scale,
+                                            int mod_stride, const float* stats, float* dx, int accumulate,
+                                            float* dshift, float* dscale, int dmod_stride, const void* y,
+                                            const float* gate, int gate_stride, void* dy, float* dgate,
+                                            int dgate_stride, float* dbias, int B, int T, int D, void* stream) {
+  DITB_REQUIRE(dh && x && scale && stats && dx && dshift && dscale, DITB200_EINVAL, "ln_modulate_bwd_gate: null pointer");
+  DITB_REQUIRE(y == nullptr || (gate && dy && dgate), DITB200_EINVAL, "ln_modulate_bwd_gate: y needs gate, dy and dgate");
+  DITB_REQUIRE(B > 0 && T > 0 && T % kFbRows == 0 && (D == 384 || D == 768 || D == 1024 || D == 1152), DITB200_EINVAL,
+               "ln_modulate_bwd_gate: bad shape B=%d T=%d D=%d (T %% 4 == 0, D in 384, 768, 1024, 1152)", B, T, D);
+  DITB_REQUIRE((long long)B * T * D < (1ll << 40), DITB200_EINVAL, "ln_modulate_bwd_gate: too large");
+  DITB_REQUIRE(dh_dtype == DITB200_BF16 || dh_dtype == DITB200_F32, DITB200_EINVAL, "ln_modulate_bwd_gate: bad dh_dtype");
+  DITB_REQUIRE(aligned16(dh) && aligned16(x) && aligned16(dx) && aligned16(scale) && mod_stride % 4 == 0 &&
+                   aligned16(dshift) && aligned16(dscale) && dmod_stride % 4 == 0 && aligned16(stats),
+               DITB200_EALIGN, "ln_modulate_bwd_gate: misaligned pointer or stride");
+  if (y != nullptr)
+    DITB_REQUIRE(aligned16(y) && aligned16(dy) && aligned16(gate) && gate_stride % 4 == 0 && aligned16(dgate) &&
+                     dgate_stride % 4 == 0 && (!dbias || aligned16(dbias)),
+                 DITB200_EALIGN, "ln_modulate_bwd_gate: misaligned y / dy / gate / dgate / dbias");
+  cudaStream_t st = (cudaStream_t)stream;
+#define LNG_ARGS dh, x, scale, mod_stride, stats, dx, accumulate, dshift, dscale, dmod_stride, y, gate, gate_stride, dy, dgate, dgate_stride, dbias, B, T, st
+#define LNG_CASE(NT)                                                                                           \
+  case NT * 4:                                                                                                 \
+    if (dh_dtype == DITB200_BF16)                                                                              \
+      return y ? launch_ln_bwd_cols<NT, __nv_bfloat16, true>(LNG_ARGS) : launch_ln_bwd_cols<NT, __nv_bfloat16, false>(LNG_ARGS); \
+    return y ? launch_ln_bwd_cols<NT, float, true>(LNG_ARGS) : launch_ln_bwd_cols<NT, float, false>(LNG_ARGS);
+  switch (D) {
+    LNG_CASE(96)
+    LNG_CASE(192)
+    LNG_CASE(256)
+    LNG_CASE(288)
+  }
+#undef LNG_CASE
+#undef LNG_ARGS
+  return DITB200_EINVAL;
+}
+
 extern "C" int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_dtype, const float* gate,
                                       int gate_stride, void* dy, int dy_dtype, float* dgate, int dgate_stride,
                                       float* dbias, int B, int T, int D, void* stream) {
@@ -450,6 +745,20 @@ extern "C" int ditb200_colsum(const void* in, int dtype, float* out, int accumul
       colsum4_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), out, R, C);
   }
   DITB_LAUNCH_CHECK("colsum");
+  return 0;
+}
+
+extern "C" int ditb200_adaln_wgrad(const float* dmod, int dmod_stride, const void* sc, float* dw, float* dbias, int N,
+                                   int R, int D, void* stream) {
+  DITB_REQUIRE(dmod && sc && dw, DITB200_EINVAL, "adaln_wgrad: null pointer");
+  DITB_REQUIRE(N > 0 && R > 0 && D > 0 && R % kAwRows == 0 && D % kAwCols == 0 && R / kAwRows <= 65535 * 32, DITB200_EINVAL,
+               "adaln_wgrad: bad shape N=%d R=%d D=%d (R %% 64 == 0, D %% 128 == 0)", N, R, D);
+  DITB_REQUIRE(aligned16(dmod) && dmod_stride % 4 == 0 && aligned16(sc) && aligned16(dw) && (!dbias || aligned16(dbias)),
+               DITB200_EALIGN, "adaln_wgrad: misaligned pointer or stride");
+  dim3 grid(R / kAwRows, D / kAwCols);
+  DITB_KLAUNCH((adaln_wgrad_kernel), grid, dim3(256), 0, (cudaStream_t)stream, dmod, dmod_stride,
+               reinterpret_cast<const __nv_bfloat16*>(sc), dw, dbias, N, R, D);
+  DITB_LAUNCH_CHECK("adaln_wgrad");
   return 0;
 }
 

@@ -13,18 +13,11 @@ namespace ditb200 {
 // warp-level load/store is a contiguous 512-byte segment.  The row stays in registers between
 // the statistics pass and the normalise pass: x is read from HBM exactly once.
 template <int NV, bool kOutBf16>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x,
-                                                          const float* __restrict__ shift,
-                                                          const float* __restrict__ scale,
-                                                          int mod_stride, void* __restrict__ out,
-                                                          float* __restrict__ stats, int M, int T,
-                                                          float eps, int reverse) {
-  DITB_PDL_WAIT();
+__device__ __forceinline__ void ln_modulate_row(const float* __restrict__ x, const float* __restrict__ shift,
+                                                const float* __restrict__ scale, int mod_stride,
+                                                void* __restrict__ out, float* __restrict__ stats, int row, int T,
+                                                float eps, int lane) {
   constexpr int D = NV * 128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int row = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= M) return;
-  if (reverse) row = M - 1 - row;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   float4 v[NV];
 #pragma unroll
@@ -68,20 +61,29 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restric
   }
 }
 
+template <int NV, bool kOutBf16>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const float* __restrict__ x,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ scale,
+                                                          int mod_stride, void* __restrict__ out,
+                                                          float* __restrict__ stats, int M, int T,
+                                                          float eps, int reverse) {
+  DITB_PDL_WAIT();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  ln_modulate_row<NV, kOutBf16>(x, shift, scale, mod_stride, out, stats, reverse ? M - 1 - row : row, T, eps, lane);
+}
+
 // Gated residual update + LayerNorm + modulate in one pass (training forward): x_out = x + gate[b] * y is formed
 // in registers from the f32 stream and the bf16 branch output, written back once, and normalised / modulated
 // from the same registers.
 template <int NV, bool kOutBf16>
-__global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
+__device__ __forceinline__ void ln_modulate_resid_row(
     const float* __restrict__ x, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
     const float* __restrict__ shift, const float* __restrict__ scale, int mod_stride, float* __restrict__ x_out,
-    void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps, int reverse) {
-  DITB_PDL_WAIT();
+    void* __restrict__ out, float* __restrict__ stats, int row, int T, float eps, int lane) {
   constexpr int D = NV * 128;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int row = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= M) return;
-  if (reverse) row = M - 1 - row;
   const int b = row / T;
   const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
   const uint2* yr = reinterpret_cast<const uint2*>(y + (size_t)row * D);
@@ -134,6 +136,19 @@ __global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
       reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * D)[lane + 32 * j] = o;
     }
   }
+}
+
+template <int NV, bool kOutBf16>
+__global__ void __launch_bounds__(128) ln_modulate_resid_kernel(
+    const float* __restrict__ x, const __nv_bfloat16* __restrict__ y, const float* __restrict__ gate,
+    const float* __restrict__ shift, const float* __restrict__ scale, int mod_stride, float* __restrict__ x_out,
+    void* __restrict__ out, float* __restrict__ stats, int M, int T, float eps, int reverse) {
+  DITB_PDL_WAIT();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= M) return;
+  ln_modulate_resid_row<NV, kOutBf16>(x, y, gate, shift, scale, mod_stride, x_out, out, stats,
+                                      reverse ? M - 1 - row : row, T, eps, lane);
 }
 
 // Any D % 4 == 0: same mapping, row re-read from L1/L2 instead of held in registers.
@@ -561,11 +576,9 @@ extern "C" int ditb200_ln_modulate(const float* x, const float* shift, const flo
 #define LN_CASE(NV)                                                                              \
   case NV * 128:                                                                                 \
     if (bf)                                                                                      \
-      DITB_KLAUNCH((ln_modulate_kernel<NV, true>), grid, block, 0, st, x, shift, scale, mod_stride, out,     \
-                                                           stats, M, T, eps, reverse);           \
+      DITB_KLAUNCH((ln_modulate_kernel<NV, true>), grid, block, 0, st, x, shift, scale, mod_stride, out, stats, M, T, eps, reverse); \
     else                                                                                         \
-      DITB_KLAUNCH((ln_modulate_kernel<NV, false>), grid, block, 0, st, x, shift, scale, mod_stride, out,    \
-                                                            stats, M, T, eps, reverse);          \
+      DITB_KLAUNCH((ln_modulate_kernel<NV, false>), grid, block, 0, st, x, shift, scale, mod_stride, out, stats, M, T, eps, reverse); \
     break;
   switch (D) {
     LN_CASE(3)
@@ -604,11 +617,9 @@ extern "C" int ditb200_ln_modulate_resid(const float* x, const void* y, const fl
 #define LNR_CASE(NV)                                                                                                  \
   case NV * 128:                                                                                                      \
     if (bf)                                                                                                           \
-      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, true>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,   \
-                                                                 stats, M, T, eps, reverse);                          \
+      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, true>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out, stats, M, T, eps, reverse); \
     else                                                                                                              \
-      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, false>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out,  \
-                                                                  stats, M, T, eps, reverse);                         \
+      DITB_KLAUNCH((ln_modulate_resid_kernel<NV, false>), grid, block, 0, st, x, yb, gate, shift, scale, mod_stride, x_out, out, stats, M, T, eps, reverse); \
     break;
   switch (D) {
     LNR_CASE(3)

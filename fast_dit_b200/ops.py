@@ -396,6 +396,31 @@ def ln_modulate_bwd(dh, x, scale, stats, T: int, dx, accumulate: bool, dshift, d
     return dx
 
 
+def ln_modulate_bwd_gate_ok(T: int, D: int) -> bool:
+    """Shapes the fused LayerNorm-backward + gated-residual-backward kernel serves."""
+    return T % 4 == 0 and D in (384, 768, 1024, 1152)
+
+
+def ln_modulate_bwd_gate(dh, x, scale, stats, T: int, dx, accumulate: bool, dshift, dscale, y=None, gate=None,
+                         dgate=None, dbias=None, dy=None):
+    """ln_modulate_bwd, then — on the dx just formed, in the same pass — gate_resid_bwd of the branch y (bf16) that
+    joined the stream in front of this LayerNorm: dy = dx * gate[b]; dgate += sum_t dx * y; dbias += colsum(dy).
+    Returns (dx, dy); y=None: only the LayerNorm part."""
+    lib = _lib_for(x)
+    _chk_contig(dh, x, stats, dx, y, dy, dbias)
+    M, D = x.shape
+    assert scale.stride(1) == 1 and dshift.stride(1) == 1 and dscale.stride(1) == 1 and dshift.stride(0) == dscale.stride(0)
+    if y is not None:
+        assert y.dtype == torch.bfloat16 and gate.stride(1) == 1 and dgate.stride(1) == 1
+        if dy is None:
+            dy = torch.empty_like(y)
+    _call("ln_modulate_bwd_gate", lib.ditb200_ln_modulate_bwd_gate, _p(dh), _DT[dh.dtype], _p(x), _p(scale),
+          scale.stride(0), _p(stats), _p(dx), int(accumulate), _p(dshift), _p(dscale), dshift.stride(0), _p(y),
+          _p(gate), gate.stride(0) if gate is not None else 0, _p(dy), _p(dgate),
+          dgate.stride(0) if dgate is not None else 0, _p(dbias), M // T, T, D, _stream())
+    return dx, dy
+
+
 def gate_resid_bwd(dx_out, y, gate, T: int, dgate, dbias=None, dy=None):
     """dy = dx_out * gate[b]; dgate += sum_t dx_out * y; dbias += colsum(dy)."""
     lib = _lib_for(dx_out)
@@ -417,6 +442,25 @@ def colsum(x, out=None, accumulate: bool = False):
         out = torch.empty(Cc, device=x.device, dtype=torch.float32)
     _call("colsum", lib.ditb200_colsum, _p(x), _DT[x.dtype], _p(out), int(accumulate), R, Cc, _stream())
     return out
+
+
+def adaln_wgrad_ok(N: int, R: int, D: int) -> bool:
+    """Shapes (and batch sizes: the kernel's cost grows with N, the tensor-core route's does not) the outer-product
+    weight-gradient kernel of the adaLN Linears serves."""
+    return N <= 256 and R % 64 == 0 and D % 128 == 0
+
+
+def adaln_wgrad(dmod, sc, dw, dbias=None):
+    """dw[r, c] = sum_b dmod[b, r] * sc[b, c]; dbias[r] = sum_b dmod[b, r].  dmod f32 [N, R] (a column slice of a wider
+    buffer is fine), sc bf16 [N, D]; dw [R, D] and dbias [R] are overwritten."""
+    lib = _lib_for(dmod)
+    _chk_contig(sc, dw, dbias)
+    N, R = dmod.shape
+    D = sc.shape[1]
+    assert dmod.stride(1) == 1 and dmod.dtype == torch.float32 and sc.dtype == torch.bfloat16 and dw.shape == (R, D)
+    _call("adaln_wgrad", lib.ditb200_adaln_wgrad, _p(dmod), dmod.stride(0), _p(sc), _p(dw), _p(dbias), N, R, D,
+          _stream())
+    return dw
 
 
 def label_embed_bwd(dc, y, dtable):

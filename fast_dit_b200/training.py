@@ -289,28 +289,75 @@ class _DiTFunction(torch.autograd.Function):
 
         w = sh["w"]
         ada_w = sh["ada_w"]
-        dsc = torch.zeros((N, D), device=dev, dtype=torch.float32)  # gradient of silu(c), summed over all adaLN layers
+        M = N * T
+        # Gradient of every adaLN output, one row per image: [blocks 0..L-1: 6 chunks each | final layer: 2 chunks].
+        # The LayerNorm / gate backward kernels reduce into its slices; the weight gradients are taken block by block
+        # (so every bucket is complete when its block is), the data gradient d silu(c) once, over all of it, at the
+        # end — unless an optimizer updates each bucket during backward (FusedAdamWEMA(overlap_backward=True), the
+        # sharded optimizer): the adaLN weights of a finished block are then no longer the ones the forward used, so
+        # every block contributes its share of d silu(c) before it hands its bucket over.
+        early_update = getattr(model, "_bucket_ready", None) is not None
+        widths = [6 * D] * Ld + [2 * D]
+        if early_update:
+            dmods = [torch.zeros((N, wd), device=dev, dtype=torch.float32) for wd in widths]
+            dsc = torch.zeros((N, D), device=dev, dtype=torch.float32)
+        else:
+            dmod_all = torch.zeros((N, sum(widths)), device=dev, dtype=torch.float32)
+            dmods = [dmod_all[:, 6 * D * i:6 * D * i + wd] for i, wd in enumerate(widths)]
+        simt_ada = ops.adaln_wgrad_ok(N, 2 * D, D)  # 6 * D and 2 * D divide alike
 
         def ada_bwd(dmod, w_rows, lin):
-            """adaLN_modulation[1] backward: weight/bias gradients and the contribution to d silu(c)."""
-            dmod_bf = ops.cast_bf16(dmod)
-            ops.gemm(dmod_bf, sc, None, out=G(lin.weight), trans_a=True, trans_w=True)
-            ops.colsum(dmod, out=G(lin.bias))
-            ops.gemm(dmod_bf, w_rows, None, out=dsc, trans_w=True, accumulate=True,
-                     split_k=_split_k(N, D, dmod.shape[1], True))
+            """adaLN_modulation[1] backward: weight and bias gradients of one Linear (and, in early-update mode, its
+            contribution to d silu(c))."""
+            dmod_bf = None
+            if simt_ada:
+                ops.adaln_wgrad(dmod, sc, G(lin.weight), G(lin.bias))
+            else:
+                dmod = dmod.contiguous()
+                dmod_bf = ops.cast_bf16(dmod)
+                ops.gemm(dmod_bf, sc, None, out=G(lin.weight), trans_a=True, trans_w=True)
+                ops.colsum(dmod, out=G(lin.bias))
+            if early_update:
+                ops.gemm(dmod_bf if dmod_bf is not None else ops.cast_bf16(dmod), w_rows, None, out=dsc, trans_w=True,
+                         accumulate=True, split_k=_split_k(N, D, dmod.shape[1], True))
+
+        # Every LayerNorm backward completes the gradient of the residual stream at its point of the chain, and the
+        # next consumer of that gradient is the gated-residual backward of the branch that joined the stream just
+        # before that LayerNorm (the previous block's MLP branch, or this block's attention branch): one fused pass
+        # where the shapes allow it (ops.ln_modulate_bwd_gate), the two kernels otherwise.
+        fuse_gate = ops.ln_modulate_bwd_gate_ok(T, D)
+        dtok = torch.empty((M, D), device=dev, dtype=torch.float32)
+
+        def ln_bwd(dh, x_ln, scale, stats, accumulate, dshift, dscale, branch):
+            """branch = (y, gate, dgate, bias parameter) of the gated residual whose backward comes next, or None.
+            Returns that branch's dy."""
+            if branch is None:
+                ops.ln_modulate_bwd(dh, x_ln, scale, stats, T, dtok, accumulate, dshift, dscale)
+                return None
+            yb, gate, dgate, bias = branch
+            gb = G(bias).zero_()
+            if fuse_gate:
+                return ops.ln_modulate_bwd_gate(dh, x_ln, scale, stats, T, dtok, accumulate, dshift, dscale,
+                                                y=yb, gate=gate, dgate=dgate, dbias=gb)[1]
+            ops.ln_modulate_bwd(dh, x_ln, scale, stats, T, dtok, accumulate, dshift, dscale)
+            return ops.gate_resid_bwd(dtok, yb, gate, T, dgate, dbias=gb)
+
+        def mlp_branch(i):
+            """The MLP branch of block i as the gate backward needs it."""
+            m = mod[:, i * 6 * D:(i + 1) * 6 * D]
+            return (ctx.saved[i][12], m[:, 5 * D:6 * D], dmods[i][:, 5 * D:6 * D], model.blocks[i].mlp.fc2.bias)
 
         # ---------------- final layer (models_original.py:138-142, 218-231)
         fl = model.final_layer
         mf = mod[:, Ld * 6 * D:]
         dz = ops.unpatchify_bwd(dout.float().contiguous(), p)
-        stf = torch.empty((N * T, 2), device=dev, dtype=torch.float32)
+        stf = torch.empty((M, 2), device=dev, dtype=torch.float32)
         hf = ops.ln_modulate(tok_final, mf[:, :D], mf[:, D:], T, out_dtype=bf, stats=stf)
         _wgrad(dz, hf, G(fl.linear.weight))
         ops.colsum(dz, out=G(fl.linear.bias))
         dhf = _dgrad(dz, ops.cast_bf16(fl.linear.weight.detach()))
-        dmod_f = torch.zeros((N, 2 * D), device=dev, dtype=torch.float32)
-        dtok = torch.empty((N * T, D), device=dev, dtype=torch.float32)
-        ops.ln_modulate_bwd(dhf, tok_final, mf[:, D:], stf, T, dtok, False, dmod_f[:, :D], dmod_f[:, D:])
+        dmod_f = dmods[Ld]
+        dy2 = ln_bwd(dhf, tok_final, mf[:, D:], stf, False, dmod_f[:, :D], dmod_f[:, D:], mlp_branch(Ld - 1))
         ada_bwd(dmod_f, ada_w[Ld * 6 * D:], fl.adaLN_modulation[1])
         del dz, hf, dhf
         sync("final_layer", arena)
@@ -319,34 +366,34 @@ class _DiTFunction(torch.autograd.Function):
         for i in range(Ld - 1, -1, -1):
             blk = model.blocks[i]
             x_in, st1, hA, qkv, lse, o, y1, x_mid, st2, hB, a1, u, y2 = ctx.saved[i]
-            ctx.saved[i] = None
             m = mod[:, i * 6 * D:(i + 1) * 6 * D]
-            sc1, g1, sc2, g2 = m[:, D:2 * D], m[:, 2 * D:3 * D], m[:, 4 * D:5 * D], m[:, 5 * D:6 * D]
-            dmod = torch.zeros((N, 6 * D), device=dev, dtype=torch.float32)
+            sc1, g1, sc2 = m[:, D:2 * D], m[:, 2 * D:3 * D], m[:, 4 * D:5 * D]
+            dmod = dmods[i]
             dm = [dmod[:, j * D:(j + 1) * D] for j in range(6)]
-            # x_out = x_mid + g2 * fc2(gelu(fc1(modulate(LN(x_mid)))))
-            gb = G(blk.mlp.fc2.bias).zero_()
-            dy2 = ops.gate_resid_bwd(dtok, y2, g2, T, dm[5], dbias=gb)
+            # x_out = x_mid + g2 * fc2(gelu(fc1(modulate(LN(x_mid))))); dy2 = g2 * d x_out came with the previous kernel
             _wgrad(dy2, u, G(blk.mlp.fc2.weight))
             da1 = _dgrad(dy2, w[4 * i + 3], epilogue=L.EPI_MUL_AUX, aux_in=a1)
             _wgrad(da1, hB, G(blk.mlp.fc1.weight))
             ops.colsum(da1, out=G(blk.mlp.fc1.bias))
             dh = _dgrad(da1, w[4 * i + 2])
-            ops.ln_modulate_bwd(dh, x_mid, sc2, st2, T, dtok, True, dm[3], dm[4])
+            dy1 = ln_bwd(dh, x_mid, sc2, st2, True, dm[3], dm[4], (y1, g1, dm[2], blk.attn.proj.bias))
             del dy2, da1, dh, y2, u, a1, hB
             # x_mid = x_in + g1 * proj(attention(qkv(modulate(LN(x_in)))))
-            gb = G(blk.attn.proj.bias).zero_()
-            dy1 = ops.gate_resid_bwd(dtok, y1, g1, T, dm[2], dbias=gb)
             _wgrad(dy1, o, G(blk.attn.proj.weight))
             do = _dgrad(dy1, w[4 * i + 1])
             dqkv = ops.attention_bwd(qkv, o, do, lse, N, T, Hh, hd)
             _wgrad(dqkv, hA, G(blk.attn.qkv.weight))
             ops.colsum(dqkv, out=G(blk.attn.qkv.bias))
             dh = _dgrad(dqkv, w[4 * i])
-            ops.ln_modulate_bwd(dh, x_in, sc1, st1, T, dtok, True, dm[0], dm[1])
+            dy2 = ln_bwd(dh, x_in, sc1, st1, True, dm[0], dm[1], mlp_branch(i - 1) if i > 0 else None)
+            ctx.saved[i] = None
             ada_bwd(dmod, ada_w[i * 6 * D:(i + 1) * 6 * D], blk.adaLN_modulation[1])
             del dy1, do, dqkv, dh
             sync(f"blocks.{i}", arena)
+
+        if not early_update:  # d silu(c), summed over every adaLN layer: one long-K GEMM over the whole modulation gradient
+            dsc = ops.gemm(ops.cast_bf16(dmod_all), ada_w, None, out_dtype=torch.float32, trans_w=True,
+                           split_k=_split_k(N, D, dmod_all.shape[1], True))
 
         # ---------------- embedders (models_original.py:240-243)
         pe = model.x_embedder.proj

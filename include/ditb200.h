@@ -161,6 +161,18 @@ int ditb200_ln_modulate_bwd(const void* dh, int dh_dtype, const float* x, const 
                             const float* stats, float* dx, int accumulate, float* dshift, float* dscale,
                             int dmod_stride, int B, int T, int D, void* stream);
 
+/* ditb200_ln_modulate_bwd followed, in the same pass over the rows, by ditb200_gate_resid_bwd of the branch that
+ * joined the residual stream in front of this LayerNorm (models_original.py:120-121 read backwards: the gradient
+ * of the stream this call completes, dx, is what that branch's backward consumes):
+ *   dx (+)= LayerNorm+modulate backward as above;  dshift / dscale += ...
+ *   y != NULL:  dy[B*T, D] (bf16) = dx * gate[b];  dgate[b, :] += sum_t dx[b,t,:] * y[b,t,:];  dbias[:] += sum dy
+ * y == NULL: only the LayerNorm part.  y, dy bf16 [B*T, D]; the reductions are atomics onto caller-zeroed f32 rows.
+ * T % 4 == 0 and D in {384, 768, 1024, 1152}; other shapes: call the two entries above / below one after the other. */
+int ditb200_ln_modulate_bwd_gate(const void* dh, int dh_dtype, const float* x, const float* scale, int mod_stride,
+                                 const float* stats, float* dx, int accumulate, float* dshift, float* dscale,
+                                 int dmod_stride, const void* y, const float* gate, int gate_stride, void* dy,
+                                 float* dgate, int dgate_stride, float* dbias, int B, int T, int D, void* stream);
+
 /* Backward of the gated-residual epilogue x_out = x + gate[b] * y (models_original.py:120-121):
  * dy[B*T, D] (dy_dtype == y_dtype) = dx_out * gate[b];  dgate[b, :] += sum_t dx_out[b,t,:] * y[b,t,:];
  * dbias[:] += sum over all tokens of dy (the bias gradient of the Linear that produced y; may be NULL).
@@ -173,6 +185,15 @@ int ditb200_gate_resid_bwd(const float* dx_out, const void* y, int y_dtype, cons
 /* out[C] f32 (+)= column sums of in[R, C] (dtype): bias gradients of the QKV / fc1 / embedding Linears.
  * C % 4 == 0.  accumulate == 0 zeroes out first. */
 int ditb200_colsum(const void* in, int dtype, float* out, int accumulate, int R, int C, void* stream);
+
+/* Weight and bias gradient of an adaLN modulation Linear (models_original.py:113-116, 128-131 backward):
+ *   dw[r, c] = sum_b dmod[b, r] * sc[b, c];   dbias[r] = sum_b dmod[b, r]   (dbias may be NULL)
+ * dmod f32 [N, R] with row stride dmod_stride (the buffer the LayerNorm / gate backward kernels reduce into),
+ * sc bf16 [N, D] = silu(c) as the forward read it, dw f32 [R, D] and dbias f32 [R] are OVERWRITTEN.
+ * The contraction runs over the batch only: an outer-product kernel bound by the store of dw.
+ * R % 64 == 0 and D % 128 == 0. */
+int ditb200_adaln_wgrad(const float* dmod, int dmod_stride, const void* sc, float* dw, float* dbias, int N, int R,
+                        int D, void* stream);
 
 /* dtable[y[b], :] += dc[b, :] (f32 atomics): backward of the label-embedding gather. */
 int ditb200_label_embed_bwd(const float* dc, const int64_t* y, float* dtable, int B, int D, int num_rows,

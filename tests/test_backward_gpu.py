@@ -124,6 +124,75 @@ def test_ln_modulate_bwd(ops, dev, D, T, dh_dtype):
     assert rel_l2(dx2, xd.grad) < 2e-5
 
 
+@pytest.mark.parametrize("D,T,B", [(384, 36, 3), (1152, 256, 5), (768, 64, 40), (1024, 8, 2), (1152, 4, 1)])
+@pytest.mark.parametrize("dh_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("with_gate", [True, False])
+def test_ln_modulate_bwd_gate_fused(ops, dev, D, T, B, dh_dtype, with_gate):
+    """The fused LayerNorm-backward + next gated-residual-backward kernel against the fp64 formulas, and against the two
+    separate kernels it replaces (training.py's backward chain); B * T / 4 row batches over a persistent grid, so
+    (768, 64, 40) makes CTAs cross image boundaries and flush their column sums in between."""
+    assert ops.ln_modulate_bwd_gate_ok(T, D)
+    g = _g(14)
+    x = (torch.randn(B * T, D, device=dev, generator=g) * 2 + 0.3)
+    mod = torch.randn(B, 6 * D, device=dev, generator=g) * 0.5
+    shift, scale, gate = mod[:, :D], mod[:, D:2 * D], mod[:, 2 * D:3 * D]
+    dh = torch.randn(B * T, D, device=dev, generator=g).to(dh_dtype)
+    y = torch.randn(B * T, D, device=dev, generator=g).bfloat16()
+    stats = torch.empty(B * T, 2, device=dev)
+    ops.ln_modulate(x, shift, scale, T, out_dtype=torch.float32, stats=stats)
+    xd = x.double().requires_grad_(True)
+    sd = shift.double().clone().requires_grad_(True)
+    cd = scale.double().clone().requires_grad_(True)
+    h = F.layer_norm(xd, (D,), eps=1e-6).view(B, T, D) * (1 + cd[:, None]) + sd[:, None]
+    h.backward(dh.double().view(B, T, D))
+    prev = torch.randn(B * T, D, device=dev, generator=g)
+    for accumulate in (True, False):
+        want_dx = xd.grad + (prev.double() if accumulate else 0)
+        dmod = torch.zeros(B, 6 * D, device=dev)
+        dbias = torch.zeros(D, device=dev)
+        dx0 = prev.clone() if accumulate else torch.full_like(prev, float("nan"))
+        kw = dict(y=y, gate=gate, dgate=dmod[:, 2 * D:3 * D], dbias=dbias) if with_gate else {}
+        dx, dy = ops.ln_modulate_bwd_gate(dh, x, scale, stats, T, dx0, accumulate, dmod[:, :D], dmod[:, D:2 * D], **kw)
+        assert rel_l2(dx, want_dx) < 2e-5
+        assert rel_l2(dmod[:, :D], sd.grad) < 2e-5
+        assert rel_l2(dmod[:, D:2 * D], cd.grad) < 2e-5
+        if not with_gate:
+            assert dy is None and float(dmod[:, 2 * D:].abs().max()) == 0.0
+            continue
+        want_dy = want_dx.view(B, T, D) * gate.double()[:, None]
+        assert rel_l2(dy.float(), want_dy.view(B * T, D)) < 4e-3
+        assert rel_l2(dmod[:, 2 * D:3 * D], (want_dx * y.double()).view(B, T, D).sum(1)) < 2e-5
+        assert rel_l2(dbias, want_dy.sum((0, 1))) < 2e-5
+        assert float(dmod[:, 3 * D:].abs().max()) == 0.0
+        # the two kernels it replaces, on the same inputs: same dx to rounding, the same bf16 dy almost everywhere
+        dmod2 = torch.zeros(B, 6 * D, device=dev)
+        dbias2 = torch.zeros(D, device=dev)
+        dx2 = ops.ln_modulate_bwd(dh, x, scale, stats, T, prev.clone() if accumulate else torch.empty_like(prev),
+                                  accumulate, dmod2[:, :D], dmod2[:, D:2 * D])
+        dy2 = ops.gate_resid_bwd(dx2, y, gate, T, dmod2[:, 2 * D:3 * D], dbias=dbias2)
+        assert rel_l2(dx, dx2) < 1e-6 and rel_l2(dy.float(), dy2.float()) < 1e-3
+        assert rel_l2(dmod, dmod2) < 1e-5 and rel_l2(dbias, dbias2) < 1e-5
+
+
+@pytest.mark.parametrize("N,D,chunks", [(32, 1152, 6), (5, 384, 2), (70, 768, 6), (256, 128, 1)])
+def test_adaln_wgrad(ops, dev, N, D, chunks):
+    """Outer-product weight / bias gradient of an adaLN Linear, reading a column slice of a wider f32 buffer."""
+    g = _g(15)
+    R = chunks * D
+    assert ops.adaln_wgrad_ok(N, R, D)
+    wide = torch.randn(N, R + 2 * D, device=dev, generator=g)
+    dmod = wide[:, D:D + R]
+    sc = torch.randn(N, D, device=dev, generator=g).bfloat16()
+    dw = torch.full((R, D), float("nan"), device=dev)
+    db = torch.full((R,), float("nan"), device=dev)
+    ops.adaln_wgrad(dmod, sc, dw, db)
+    assert rel_l2(dw, dmod.double().t() @ sc.double()) < 1e-6
+    assert rel_l2(db, dmod.double().sum(0)) < 1e-6
+    dw2 = torch.full((R, D), float("nan"), device=dev)
+    ops.adaln_wgrad(dmod, sc, dw2)
+    assert torch.equal(dw, dw2)
+
+
 @pytest.mark.parametrize("D,T", [(384, 37), (1152, 256)])
 def test_gate_resid_bwd(ops, dev, D, T):
     g = _g(5)
