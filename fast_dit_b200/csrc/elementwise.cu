@@ -820,6 +820,199 @@ __global__ void __launch_bounds__(256) final_layer_rows_kernel(
   }
 }
 
+// ---- 32-output variant on the tensor cores (round 2).  The SIMT kernel above is bound by re-reading the [32, D]
+// weight from shared memory for every row pair (84 us for a 75 MB read at C3).  Here a CTA takes 16 token rows at
+// a time and its 8 warps split the D columns: each lane holds its slice of two rows (g and g + 8 of the
+// m16n8k8 fragment) in registers — read from HBM once, the next tile's slice already in flight — so mean and
+// variance are exact two-pass sums (quad shuffles + one shared exchange each), the normalised, modulated values
+// become A fragments directly, and the 16 x 32 x D/8 product per warp runs as mma.sync TF32 x 3 (a = hi + lo, w =
+// hi + lo; lo*hi + hi*lo + hi*hi: fp32-accurate, this layer is kept at full precision).  The k index of a fragment
+// slot is permuted (slot t / t + 4 of step 2j / 2j + 1 = column 16j + 4t + {0, 1} / {2, 3} of the warp's slice) so that
+// both operands are read as 128-bit vectors: x from global memory, w from a [32][D + 16] shared array whose row
+// stride (16 mod 32 floats) makes the quarter-warp reads conflict-free.  The 8 partial tiles meet in shared memory
+// and leave through 128-byte segments of the NCHW image (unpatchify).
+// f = hi + lo with hi = f rounded to TF32 (10 mantissa bits) and lo the exact remainder, which the tensor core reads
+// truncated to TF32 again.  Three ALU instructions (cvt.rna.tf32.f32 compiles to ~10 with its NaN handling, and this
+// kernel's instruction stream is what bounds it): add half an ulp to the bit pattern, clear the 13 low bits, subtract.
+__device__ __forceinline__ void split_tf32(float f, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(f) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(f - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr int kFtRows = 16, kFtOStride = 40;
+template <int D>
+__global__ void __launch_bounds__(256, 1) final_layer_tc_kernel(
+    const float* __restrict__ x, const float* __restrict__ shift, const float* __restrict__ scale,
+    int mod_stride, const float* __restrict__ w, const float* __restrict__ bias,
+    float* __restrict__ out, int M, int T, int p, int Cout, float eps, int chunk) {
+  DITB_PDL_WAIT();
+  constexpr int KW = D / 8;    // columns per warp
+  constexpr int NJ = KW / 16;  // 16-column steps per warp (two k steps of the MMA each)
+  constexpr int WS = D + 16;   // padded weight row
+  static_assert(KW % 16 == 0 && WS % 32 == 16, "slice / stride assumptions");
+  extern __shared__ float ftsm[];
+  float* ws = ftsm;                          // [32][WS]
+  float* red_s = ws + 32 * WS;               // [2][8 warps][16 rows]
+  float* red_o = red_s + 2 * 8 * kFtRows;    // [8 warps][16 rows][kFtOStride]
+  float* smod = red_o + 8 * kFtRows * kFtOStride;  // [2 images][shift | scale][D]: the (at most two, T >= 16) images of a tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  auto cp16 = [](float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  for (int i = tid; i < 32 * (D / 4); i += 256) {  // the weight as asynchronous copies: all 36 per thread in flight at once
+    const int n = i / (D / 4), k4 = i - n * (D / 4);
+    cp16(ws + n * WS + 4 * k4, w + (size_t)n * D + 4 * k4);
+  }
+  const int ntiles = (M + kFtRows - 1) / kFtRows;
+  const int tile0 = blockIdx.x * chunk, tile1 = min(ntiles, tile0 + chunk);  // a contiguous range: few image changes
+  const int kbase = warp * KW + 4 * t;  // this lane's first column
+  const int Wp = (int)(sqrtf((float)T) + 0.5f), Himg = Wp * p;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 xa[NJ], xb[NJ];  // rows g and g + 8 of the current tile, this lane's columns
+  auto load_tile = [&](int tile, float4 (&A)[NJ], float4 (&Bv)[NJ]) {
+    const int ra = tile * kFtRows + g, rb = ra + 8;
+    const float4* pa = reinterpret_cast<const float4*>(x + (size_t)(ra < M ? ra : 0) * D + kbase);
+    const float4* pb = reinterpret_cast<const float4*>(x + (size_t)(rb < M ? rb : 0) * D + kbase);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      A[j] = ra < M ? ldg_stream_f4(pa + 4 * j) : zero4;
+      Bv[j] = rb < M ? ldg_stream_f4(pb + 4 * j) : zero4;
+    }
+  };
+  if (tile0 < tile1) load_tile(tile0, xa, xb);
+  int img0 = -1, img1 = -1;  // images whose shift / scale rows sit in smod[0] / smod[1]
+  for (int tile = tile0; tile < tile1; ++tile) {
+    float4 na[NJ], nb[NJ];
+    if (tile + 1 < tile1) load_tile(tile + 1, na, nb);  // in flight under this tile's arithmetic
+    // ---- the tile's images: shift and scale rows into shared memory when they change (block-uniform decision)
+    const int b_lo = (tile * kFtRows) / T, b_hi = min(tile * kFtRows + kFtRows - 1, M - 1) / T;
+    if (b_lo != img0 || b_hi != img1) {
+      __syncthreads();  // the previous tile's readers of smod are done
+      for (int i = tid; i < 4 * (D / 4); i += 256) {
+        const int row = i / (D / 4), k4 = i - row * (D / 4);  // row = image slot * 2 + (0 shift | 1 scale)
+        const int bimg = row < 2 ? b_lo : b_hi;
+        cp16(smod + row * D + 4 * k4, ((row & 1) ? scale : shift) + (size_t)bimg * mod_stride + 4 * k4);
+      }
+      img0 = b_lo, img1 = b_hi;
+    }
+    // ---- mean
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      sa += (xa[j].x + xa[j].y) + (xa[j].z + xa[j].w);
+      sb += (xb[j].x + xb[j].y) + (xb[j].z + xb[j].w);
+    }
+    sa += __shfl_xor_sync(0xffffffffu, sa, 1), sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+    sa += __shfl_xor_sync(0xffffffffu, sa, 2), sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+    if (t == 0) red_s[warp * kFtRows + g] = sa, red_s[warp * kFtRows + g + 8] = sb;
+    asm volatile("cp.async.wait_all;" ::: "memory");  // weight (first tile) and shift / scale copies of this thread
+    __syncthreads();
+    float ma = 0.f, mb = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) ma += red_s[w8 * kFtRows + g], mb += red_s[w8 * kFtRows + g + 8];
+    ma *= 1.0f / D, mb *= 1.0f / D;
+    // ---- variance (second pass over the registers)
+    float qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float d0 = xa[j].x - ma, d1 = xa[j].y - ma, d2 = xa[j].z - ma, d3 = xa[j].w - ma;
+      qa += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      d0 = xb[j].x - mb, d1 = xb[j].y - mb, d2 = xb[j].z - mb, d3 = xb[j].w - mb;
+      qb += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    qa += __shfl_xor_sync(0xffffffffu, qa, 1), qb += __shfl_xor_sync(0xffffffffu, qb, 1);
+    qa += __shfl_xor_sync(0xffffffffu, qa, 2), qb += __shfl_xor_sync(0xffffffffu, qb, 2);
+    float* red_q = red_s + 8 * kFtRows;
+    if (t == 0) red_q[warp * kFtRows + g] = qa, red_q[warp * kFtRows + g + 8] = qb;
+    __syncthreads();
+    float va = 0.f, vb = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) va += red_q[w8 * kFtRows + g], vb += red_q[w8 * kFtRows + g + 8];
+    const float ra_ = 1.0f / sqrtf(va * (1.0f / D) + eps), rb_ = 1.0f / sqrtf(vb * (1.0f / D) + eps);
+    // ---- modulate, split, multiply
+    const int row_a = min(tile * kFtRows + g, M - 1), row_b = min(tile * kFtRows + g + 8, M - 1);
+    const float* moda = smod + (row_a / T == b_lo ? 0 : 2 * D) + kbase;  // [shift | scale] of row g's image
+    const float* modb = smod + (row_b / T == b_lo ? 0 : 2 * D) + kbase;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float4 h4a = *reinterpret_cast<const float4*>(moda + 16 * j);
+      const float4 c4a = *reinterpret_cast<const float4*>(moda + D + 16 * j);
+      const float4 h4b = *reinterpret_cast<const float4*>(modb + 16 * j);
+      const float4 c4b = *reinterpret_cast<const float4*>(modb + D + 16 * j);
+      float ha[4], hb[4];
+      ha[0] = (xa[j].x - ma) * ra_ * (1.0f + c4a.x) + h4a.x, ha[1] = (xa[j].y - ma) * ra_ * (1.0f + c4a.y) + h4a.y;
+      ha[2] = (xa[j].z - ma) * ra_ * (1.0f + c4a.z) + h4a.z, ha[3] = (xa[j].w - ma) * ra_ * (1.0f + c4a.w) + h4a.w;
+      hb[0] = (xb[j].x - mb) * rb_ * (1.0f + c4b.x) + h4b.x, hb[1] = (xb[j].y - mb) * rb_ * (1.0f + c4b.y) + h4b.y;
+      hb[2] = (xb[j].z - mb) * rb_ * (1.0f + c4b.z) + h4b.z, hb[3] = (xb[j].w - mb) * rb_ * (1.0f + c4b.w) + h4b.w;
+      uint32_t ah[4], al[4], bh[4], bl[4];  // hi / lo parts of the two rows' four columns
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_tf32(ha[q], ah[q], al[q]), split_tf32(hb[q], bh[q], bl[q]);
+      // two output tiles at a time with their MMAs interleaved: a chain of six dependent MMAs per accumulator would
+      // leave the tensor pipe waiting on its own latency
+#pragma unroll
+      for (int np = 0; np < 4; np += 2) {
+        uint32_t wh[2][4], wl[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 wq = *reinterpret_cast<const float4*>(ws + ((np + u) * 8 + g) * WS + kbase + 16 * j);
+          const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_tf32(wv[q], wh[u][q], wl[u][q]);
+        }
+        // k step 2j: slots t, t + 4 = columns +0, +1;  k step 2j + 1: columns +2, +3.  Small terms first.
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], al[0], bl[0], al[1], bl[1], wh[u][0], wh[u][1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], ah[0], bh[0], ah[1], bh[1], wl[u][0], wl[u][1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], al[2], bl[2], al[3], bl[3], wh[u][2], wh[u][3]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], ah[2], bh[2], ah[3], bh[3], wl[u][2], wl[u][3]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], ah[0], bh[0], ah[1], bh[1], wh[u][0], wh[u][1]);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) mma_tf32_16x8x8(acc[np + u], ah[2], bh[2], ah[3], bh[3], wh[u][2], wh[u][3]);
+      }
+    }
+    // ---- the 8 warps' partial [16 x 32] tiles meet in shared memory
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      *reinterpret_cast<float2*>(red_o + (warp * kFtRows + g) * kFtOStride + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(red_o + (warp * kFtRows + g + 8) * kFtOStride + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+    __syncthreads();
+    // output element e = ((c * p + pi) * 16 + token) * p + pj: consecutive threads walk along an image row (unpatchify)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int e = tid + 256 * half;
+      const int pj = e % p, r1 = e / p, tok = r1 % kFtRows, r2 = r1 / kFtRows, pi = r2 % p, c = r2 / p;
+      const int o = (pi * p + pj) * Cout + c;
+      const int row = tile * kFtRows + tok;
+      if (row < M) {
+        float v = bias[o];
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) v += red_o[(w8 * kFtRows + tok) * kFtOStride + o];
+        const int b = row / T, tt = row - b * T;
+        const int hh = tt / Wp, ww = tt - hh * Wp;
+        out[(((size_t)b * Cout + c) * Himg + hh * p + pi) * Himg + ww * p + pj] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) xa[j] = na[j], xb[j] = nb[j];
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");  // a CTA without tiles still owns its weight copies
+}
+
 extern "C" int ditb200_final_layer(const float* x, const float* shift, const float* scale,
                                    int mod_stride, const float* w, const float* bias, float* out,
                                    int B, int T, int D, int p, int Cout, float eps, int round_bf16,
@@ -837,6 +1030,32 @@ extern "C" int ditb200_final_layer(const float* x, const float* shift, const flo
   const int M = B * T;
   const dim3 grid((M + kFlRows - 1) / kFlRows), block(256);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool simt_only = getenv("DITB200_FINAL_SIMT") != nullptr;  // measurement switch: the SIMT 32-output kernel
+  if (NO == 32 && !simt_only && !round_bf16 && T >= kFtRows && aligned16(w) && (D == 384 || D == 768 || D == 1024 || D == 1152)) {
+    const size_t smem = ((size_t)32 * (D + 16) + 2 * 8 * kFtRows + (size_t)8 * kFtRows * kFtOStride + (size_t)4 * D) * sizeof(float);
+    const int ntiles = (M + kFtRows - 1) / kFtRows;
+    int g = num_sms() > 0 ? num_sms() : 148;
+    if (g > ntiles) g = ntiles;
+    const int chunk = (ntiles + g - 1) / g;
+    g = (ntiles + chunk - 1) / chunk;
+#define FTC_CASE(DD)                                                                                           \
+  case DD: {                                                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(final_layer_tc_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                           \
+    if (e != cudaSuccess) return check_cuda(e, "final_layer smem attr");                                       \
+    DITB_KLAUNCH((final_layer_tc_kernel<DD>), dim3(g), dim3(256), smem, st, x, shift, scale, mod_stride, w, bias, out, \
+                 M, T, p, Cout, eps, chunk);                                                       \
+  } break;
+    switch (D) {
+      FTC_CASE(384)
+      FTC_CASE(768)
+      FTC_CASE(1024)
+      FTC_CASE(1152)
+    }
+#undef FTC_CASE
+    DITB_LAUNCH_CHECK("final_layer");
+    return 0;
+  }
   if (NO == 32 && D % 128 == 0 && aligned16(w) && (D / 128 == 3 || D / 128 == 6 || D / 128 == 8 || D / 128 == 9)) {
     const size_t smem = (size_t)32 * D * sizeof(float);
     int g = num_sms() > 0 ? num_sms() : 148;

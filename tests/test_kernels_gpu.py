@@ -321,7 +321,8 @@ def test_attention_tcgen05_persistent(ops, dev, B, T, H, hd):
     assert torch.equal(o, again), "no atomics, fixed schedule: run-to-run identical"
 
 
-@pytest.mark.parametrize("p,Cout,T,D", [(2, 8, 256, 1152), (4, 8, 64, 768), (8, 8, 16, 384), (2, 4, 256, 384)])
+@pytest.mark.parametrize("p,Cout,T,D", [(2, 8, 256, 1152), (4, 8, 64, 768), (8, 8, 16, 384), (2, 4, 256, 384),
+                                         (2, 8, 100, 384), (2, 8, 49, 768), (2, 8, 1024, 1024), (4, 2, 64, 1152)])
 def test_final_layer(ops, dev, p, Cout, T, D):
     g = torch.Generator(device=dev).manual_seed(9)
     B = 3
