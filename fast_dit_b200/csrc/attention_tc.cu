@@ -47,7 +47,34 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]
+// D[tmem] (+)= A[smem desc] * B[smem desc]  and  D[tmem] (+)= A[tmem] * B[smem desc], with the shared-memory
+// descriptors passed as (low word, high word): the issue loops advance the low word (start address >> 4) by a
+// compile-time constant per k step, so that the one issuing thread spends one add per instruction instead of
+// rebuilding the descriptor (attn_fwd_tc_kernel: its P.V product is 32 small MMAs per query tile in a loop whose trip
+// count is a run-time value, and was bound by their issue, not by the tensor pipe: profiles/r02_attention_timeline.md)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_units) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (lbo_units << 16);
+}
+__device__ __forceinline__ void umma_bf16_ss_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_lh(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same forms with whole 64-bit descriptors (KV-blocked forward and backward: their issue loops have compile-time
+// trip counts and ptxas folds the descriptor arithmetic; the low/high split there only costs registers)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -81,6 +108,19 @@ constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (6u << 29);    // 8-
 __device__ __forceinline__ uint64_t mk_desc(uint32_t hi, uint32_t smem_addr, uint32_t lbo_units) {
   return ((uint64_t)hi << 32) | (uint64_t)(((smem_addr & 0x3FFFFu) >> 4) | (lbo_units << 16));
 }
+
+// Timeline probe (tools/attn_trace.py; -DDITB200_ATTN_TRACE builds only, the default library carries none of it):
+// CTA 0 and CTA 100 record clock64() at every hand-off of their first 8 work items.
+#ifdef DITB200_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[2 * 8 * 32];
+#define ATR(slot)                                                                                          \
+  do {                                                                                                     \
+    if ((blockIdx.x == 0 || blockIdx.x == 100) && it < 8)                                                  \
+      g_attn_trace[((blockIdx.x != 0) * 8 + it) * 32 + (slot)] = (unsigned long long)clock64();            \
+  } while (0)
+#else
+#define ATR(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_k0,
@@ -137,6 +177,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const int tok0 = b * T;
       uint8_t* kv = smem + AttnSmem::oKV + stage * AttnSmem::kKV;
       mbar_wait(&kv_empty[stage], kvpar ^ 1u);
+      if (lane == 0) ATR(20);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[stage], kv_bytes);
         tma_load_3d(&map_k0, &kv_full[stage], kv, 0, H + h, tok0);
@@ -158,6 +199,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
           tma_load_3d(&map_v0, &kv_full[stage], v0 + kb * 8192, 0, 2 * H + h, tok0 + kb * 64);
         if (has_c1) tma_load_3d(&map_kv1, &kv_full[stage], v0 + AttnSmem::kV0, 64, 2 * H + h, tok0);
       }
+      if (lane == 0) ATR(21);
       __syncwarp();
     }
   } else if (warp == 9) {
@@ -174,10 +216,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const uint32_t d = tmem_base + (uint32_t)(t * kAtRegion);
       const uint32_t q0 = smem_u32(smem + AttnSmem::oQ0 + t * AttnSmem::kQ0);
       const uint32_t q1 = smem_u32(smem + AttnSmem::oQ1 + t * AttnSmem::kQ1);
+      const uint32_t q0lo = desc_lo(q0, 0), k0lo = desc_lo(k0, 0);
 #pragma unroll
       for (int j = 0; j < 4; ++j)  // 16 channels per step = 32 bytes inside the 128-byte swizzled row
-        umma_bf16<1>(d, mk_desc(kDescHiSw128, q0 + 32 * j, 0), mk_desc(kDescHiSw128, k0 + 32 * j, 0), idesc_s, j > 0);
-      if (has_c1) umma_bf16<1>(d, mk_desc(kDescHiSw32, q1, 1), mk_desc(kDescHiSw32, k1, 1), idesc_s, 1u);
+        umma_bf16_ss_lh(d, q0lo + 2 * j, k0lo + 2 * j, kDescHiSw128, idesc_s, j > 0);
+      if (has_c1) umma_bf16_ss_lh(d, desc_lo(q1, 1), desc_lo(k1, 1), kDescHiSw32, idesc_s, 1u);
       umma_commit<1>(&s_full[t]);
       umma_commit<1>(&q_empty[t]);
     };
@@ -186,9 +229,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const uint32_t v0 = kv + AttnSmem::kK0 + AttnSmem::kK1, v1 = v0 + AttnSmem::kV0;
       const uint32_t p = tmem_base + (uint32_t)(t * kAtRegion);
       const uint32_t d = p + kAtOCol;
-      for (int ks = 0; ks < T / 16; ++ks) {  // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V
-        umma_bf16_ts(d, p + 8 * ks, mk_desc(kDescHiSw128, v0 + 2048 * ks, 0), idesc_o64, ks > 0);
-        if (has_c1) umma_bf16_ts(d + 64, p + 8 * ks, mk_desc(kDescHiSw32, v1 + 512 * ks, 1), idesc_o16, ks > 0);
+      // 16 keys per step: 8 packed TMEM columns of P, 2 KB / 512 B of V = 128 / 32 descriptor units
+      const uint32_t v0lo = desc_lo(v0, 0), v1lo = desc_lo(v1, 1);
+      if (has_c1) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_bf16_ts_lh(d, p + 8 * ks, v0lo + 128 * ks, kDescHiSw128, idesc_o64, ks > 0);
+          umma_bf16_ts_lh(d + 64, p + 8 * ks, v1lo + 32 * ks, kDescHiSw32, idesc_o16, ks > 0);
+        }
+        if (T == 256) {
+#pragma unroll
+          for (int ks = 8; ks < 16; ++ks) {
+            umma_bf16_ts_lh(d, p + 8 * ks, v0lo + 128 * ks, kDescHiSw128, idesc_o64, 1u);
+            umma_bf16_ts_lh(d + 64, p + 8 * ks, v1lo + 32 * ks, kDescHiSw32, idesc_o16, 1u);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) umma_bf16_ts_lh(d, p + 8 * ks, v0lo + 128 * ks, kDescHiSw128, idesc_o64, ks > 0);
+        if (T == 256) {
+#pragma unroll
+          for (int ks = 8; ks < 16; ++ks) umma_bf16_ts_lh(d, p + 8 * ks, v0lo + 128 * ks, kDescHiSw128, idesc_o64, 1u);
+        }
       }
       umma_commit<1>(&o_full[t]);
       if (last) umma_commit<1>(&kv_empty[stage]);
@@ -211,16 +273,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
       const uint32_t nkvpar = ((it + 1) >> 1) & 1, npar = (it + 1) & 1;
       for (int t = 0; t < nqt; ++t) {
         mbar_wait(&p_full[t], par);
+        if (lane == 0) ATR(12 + 4 * t);
         tcgen05_fence_after();
         if (elect_one()) issue_o(t, stage, t == nqt - 1);
         __syncwarp();
+        if (lane == 0) ATR(13 + 4 * t);
         if (has_next) {
           if (t == 0) mbar_wait(&kv_full[nstage], nkvpar);
           mbar_wait(&q_full[t], npar);
           mbar_wait(&s_free[t], par);  // group t has pulled O_t(i) out of the region
+          if (lane == 0) ATR(14 + 4 * t);
           tcgen05_fence_after();
           if (elect_one()) issue_s(t, nstage);
           __syncwarp();
+          if (lane == 0) ATR(15 + 4 * t);
         }
       }
     }
@@ -237,6 +303,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         const int b = wi / H, h = wi - b * H;
         const uint32_t par = it & 1;
         mbar_wait(&s_full[t], par);
+        if ((threadIdx.x & 127) == 0) ATR(6 * t);
         tcgen05_fence_after();
         // ---- pass 1: row maximum of the raw scores (TMEM loads one chunk ahead of the compare chain)
         uint32_t va[32], vb[32];
@@ -255,6 +322,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         // ---- pass 2: p = exp2((s - max) * scale * log2 e), row sum, P -> TMEM as packed bf16 (in place: the
         //      16 columns chunk c of P lands on were read as part of S chunk c/2 <= c)
         const float msc = mx * scale_log2e;
+        if ((threadIdx.x & 127) == 0) ATR(6 * t + 1);
         float2 sum2 = make_float2(0.f, 0.f);
         const float2 sl2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-msc, -msc);
         uint32_t pk[16];
@@ -284,9 +352,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         tmem_st_wait();
         tcgen05_fence_before();
         mbar_arrive(&p_full[t]);
+        if ((threadIdx.x & 127) == 0) ATR(6 * t + 2);
         // ---- output: O / sum -> bf16, transposed through this warp's staging buffer so that the global stores
         //      cover whole 64-byte row segments (8 rows per instruction) instead of 32 scattered 16-byte pieces
         mbar_wait(&o_full[t], par);
+        if ((threadIdx.x & 127) == 0) ATR(6 * t + 3);
         tcgen05_fence_after();
         uint32_t o2[16];
         tmem_ld_32x32(trow + kAtOCol, va);
@@ -295,6 +365,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         tmem_ld_wait();
         tcgen05_fence_before();
         mbar_arrive(&s_free[t]);  // the accumulators are in registers: the region may take the next score tile
+        if ((threadIdx.x & 127) == 0) ATR(6 * t + 4);
         const float inv = 1.0f / sum;
         const uint32_t stg = smem_u32(smem + AttnSmem::oStg) + (uint32_t)(warp * AttnSmem::kStg);
         __nv_bfloat16* obase = out + ((size_t)b * T + t * kAtQ + quarter * 32) * D + h * hd;
@@ -330,6 +401,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
         if (has_c1) flush(o2, 16, 64);
         if (lse != nullptr)
           lse[((size_t)b * H + h) * T + t * kAtQ + row] = (msc + log2f(sum)) * 0.6931471805599453f;
+        if ((threadIdx.x & 127) == 0) ATR(6 * t + 5);
       }
     }
   }
@@ -338,6 +410,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
   __syncthreads();
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
+#undef ATR
 
 // ============================================================================ long sequences (T > 256)
 // KV-blocked variant for T = 512, 768, 1024, ... (the 512 px configuration: 1024 tokens).  A work item is one
@@ -1038,3 +1111,12 @@ int launch_attn_fwd_tc(const void* qkv, void* out, float* lse, int B, int T, int
 }
 
 }  // namespace ditb200
+
+#ifdef DITB200_ATTN_TRACE
+// probe builds only (not declared in include/ditb200.h): copies the timeline of the last forward launch
+extern "C" int ditb200_attn_trace_read(unsigned long long* dst, int n) {
+  if (n > 2 * 8 * 32) n = 2 * 8 * 32;
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(dst, ditb200::g_attn_trace, sizeof(unsigned long long) * n);
+}
+#endif
