@@ -417,8 +417,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_cons
 // (image, head, PAIR of 128-query tiles); K and V stream through a 4-stage ring in blocks of 128 keys, each block
 // serving both query tiles.  Per query tile the score block S (128 x 128 f32) and the output accumulator O live
 // in TMEM side by side (128 + 80 columns), so the softmax is the online form:
-//   block max -> m_new, alpha = exp2((m_old - m_new) scale);  O *= alpha in TMEM (skipped when no row of the warp
-//   changed its maximum);  P = exp2((S - m_new) scale) -> TMEM over S;  l = l alpha + sum P;  O += P V_j.
+//   block max -> m_new;  when some row of the warp outgrew its reference maximum m by more than 2^8:  alpha =
+//   exp2((m - m_new) scale), O *= alpha in TMEM, l *= alpha, m = m_new (otherwise m stays: any reference keeps
+//   O / l exact as long as the exponentials stay in range);  P = exp2((S - m) scale) -> TMEM over S;
+//   l += sum P;  O += P V_j.
 // tcgen05.mma instructions of one CTA execute in issue order, which is what orders  P_j's read by PV_j  before
 // S_{j+1} overwrites it, and PV_{j-1}'s write of O before the commit that publishes S_j: no extra barriers.
 // Issue order: S(0,0) S(1,0) | PV(0,g) S(0,g+1) PV(1,g) S(1,g+1) | ... over the flattened (item, block) sequence g.
@@ -618,9 +620,14 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
         for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(va[q]), __uint_as_float(va[q + 1])));
 #pragma unroll
         for (int q = 0; q < 32; q += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(vb[q]), __uint_as_float(vb[q + 1])));
-        // ---- rescale the running output when some row of this warp moved its maximum
-        const float alpha = ex2_approx((m_run - mx) * scale_log2e);  // first block: exp2(-inf) = 0
-        if (j > 0 && __any_sync(0xffffffffu, mx > m_run)) {
+        // ---- rescale the running output — lazily: the reference maximum only has to keep exp2((s - m) scale) in
+        //      range, so it is moved (and O, l rescaled: a TMEM round trip of the accumulator on the group's chain)
+        //      only when some row of this warp outgrew it by more than 2^8; until then P is taken relative to the
+        //      stale maximum (values up to 256, same relative precision in bf16 / f32) and O / l stays exact
+        if (j == 0) {
+          m_run = mx;  // l_run = 0, and the first P.V overwrites O
+        } else if (__any_sync(0xffffffffu, (mx - m_run) * scale_log2e > 8.0f)) {
+          const float alpha = ex2_approx((m_run - mx) * scale_log2e);
           uint32_t o2[16];
           tmem_ld_32x32(trow + kKvOCol, va);
           tmem_ld_32x32(trow + kKvOCol + 32, vb);
@@ -637,11 +644,11 @@ attn_fwd_tc_kv_kernel(const __grid_constant__ CUtensorMap map_q0, const __grid_c
             for (int q = 0; q < 16; ++q) o2[q] = __float_as_uint(__uint_as_float(o2[q]) * alpha);
             tmem_st_32x16(trow + kKvOCol + 64, o2);
           }
+          l_run *= alpha;
+          m_run = mx;
         }
-        l_run *= alpha;
-        m_run = mx;
         // ---- P = exp2((S - m) scale), row sum, P -> TMEM (bf16, in place over S)
-        const float msc = mx * scale_log2e;
+        const float msc = m_run * scale_log2e;
         float2 sum2 = make_float2(0.f, 0.f);
         const float2 sl2 = make_float2(scale_log2e, scale_log2e), nm2 = make_float2(-msc, -msc);
         uint32_t pk[16];

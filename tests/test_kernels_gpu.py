@@ -321,6 +321,35 @@ def test_attention_tcgen05_persistent(ops, dev, B, T, H, hd):
     assert torch.equal(o, again), "no atomics, fixed schedule: run-to-run identical"
 
 
+@pytest.mark.parametrize("T,hd,growth", [(1024, 72, 1.0), (1024, 72, 0.25), (512, 64, 1.0), (768, 72, -1.0)])
+def test_attention_kv_blocked_running_maximum(ops, dev, T, hd, growth):
+    """The KV-blocked forward (T > 256) moves its reference maximum lazily: only when a row outgrew it by more than
+    2^8 (csrc/attention_tc.cu).  Keys whose magnitude rises with the key index make every 128-key block raise the
+    row maxima — by far more than 2^8 for growth = 1 (rescale of the running output at every block), by less for
+    growth = 0.25 (blocks evaluated against a stale maximum); growth < 0: the first block holds the maximum and
+    all later ones sit far below it."""
+    B, H = 3, 5
+    g = torch.Generator(device=dev).manual_seed(23)
+    qkv = torch.randn(B, T, 3, H, hd, device=dev, generator=g)
+    blk = torch.arange(T, device=dev) // 128
+    ramp = 1.0 + growth * blk.float() if growth > 0 else 4.0 / (1.0 + blk.float())
+    q_dir = torch.randn(B, 1, H, hd, device=dev, generator=g)
+    qkv[:, :, 0] += 2.0 * q_dir                                        # queries share a direction per head ...
+    qkv[:, :, 1] = qkv[:, :, 1] * 0.5 + q_dir * ramp[None, :, None, None]  # ... along which the keys grow block by block
+    qkv = qkv.reshape(B * T, 3 * H * hd).bfloat16()
+    lse = torch.empty(B, H, T, device=dev)
+    o = ops.attention(qkv, B, T, H, hd, lse=lse)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    q, k, _ = qkv.double().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
+    s = q @ k.transpose(-1, -2) / math.sqrt(hd)
+    bmax = s.view(B, H, T, T // 128, 128).amax(-1).cummax(-1).values     # running maximum after each block
+    jump = (bmax[..., 1:] - bmax[..., :-1]).amax() * 1.4426950408889634
+    if growth == 1.0:
+        assert jump > 8.0, "the data must push some running maximum past the 2^8 threshold"
+    assert rel_l2(o.float(), _attn_ref(qkv.float(), B, T, H, hd)) < 6e-3
+    assert rel_l2(lse, torch.logsumexp(s, dim=-1)) < 1e-4
+
+
 @pytest.mark.parametrize("p,Cout,T,D", [(2, 8, 256, 1152), (4, 8, 64, 768), (8, 8, 16, 384), (2, 4, 256, 384),
                                          (2, 8, 100, 384), (2, 8, 49, 768), (2, 8, 1024, 1024), (4, 2, 64, 1152)])
 def test_final_layer(ops, dev, p, Cout, T, D):
