@@ -450,6 +450,15 @@ def adaln_wgrad_ok(N: int, R: int, D: int) -> bool:
     return N <= 256 and R % 64 == 0 and D % 128 == 0
 
 
+def adaln_wgrad_preferred(N: int, R: int, D: int) -> bool:
+    """Whether training routes an adaLN Linear's weight gradient through the outer-product kernel rather than cast +
+    tcgen05 GEMM (K = N images) + column sum.  The kernel's time is about (0.84 + 0.064 N) ps per output element
+    (23 us at N = 32 for XL/2's 6912 x 1152, 61 us at N = 256 for B/4's 4608 x 768), the GEMM route's about 4.5 ps
+    whatever N: the crossover is near 57 images.  DITB200_ADALN_SIMT_MAX_N overrides the limit (measurement)."""
+    limit = int(os.environ.get("DITB200_ADALN_SIMT_MAX_N", "64"))
+    return adaln_wgrad_ok(N, R, D) and N <= limit
+
+
 def adaln_wgrad(dmod, sc, dw, dbias=None):
     """dw[r, c] = sum_b dmod[b, r] * sc[b, c]; dbias[r] = sum_b dmod[b, r].  dmod f32 [N, R] (a column slice of a wider
     buffer is fine), sc bf16 [N, D]; dw [R, D] and dbias [R] are overwritten."""

@@ -304,7 +304,7 @@ class _DiTFunction(torch.autograd.Function):
         else:
             dmod_all = torch.zeros((N, sum(widths)), device=dev, dtype=torch.float32)
             dmods = [dmod_all[:, 6 * D * i:6 * D * i + wd] for i, wd in enumerate(widths)]
-        simt_ada = ops.adaln_wgrad_ok(N, 2 * D, D)  # 6 * D and 2 * D divide alike
+        simt_ada = ops.adaln_wgrad_preferred(N, 2 * D, D)  # 6 * D and 2 * D divide alike
 
         def ada_bwd(dmod, w_rows, lin):
             """adaLN_modulation[1] backward: weight and bias gradients of one Linear (and, in early-update mode, its

@@ -193,6 +193,56 @@ def test_adaln_wgrad(ops, dev, N, D, chunks):
     assert torch.equal(dw, dw2)
 
 
+@pytest.mark.parametrize("N,D,chunks", [(256, 768, 6), (96, 1152, 6), (256, 384, 2)])
+def test_adaln_weight_gradient_gemm_route(ops, dev, N, D, chunks):
+    """Above ~64 images training.py takes the adaLN weight gradient through cast + tcgen05 GEMM over the batch (both
+    operands MN-major) + column sum instead of the outer-product kernel (ops.adaln_wgrad_preferred): same
+    statement as test_adaln_wgrad, through that route, and the two routes against each other."""
+    g = _g(16)
+    R = chunks * D
+    assert ops.adaln_wgrad_ok(N, R, D) and not ops.adaln_wgrad_preferred(N, R, D)
+    assert ops.adaln_wgrad_preferred(32, R, D)
+    dmod = torch.randn(N, R, device=dev, generator=g)
+    sc = torch.randn(N, D, device=dev, generator=g).bfloat16()
+    dw = torch.full((R, D), float("nan"), device=dev)
+    db = torch.full((R,), float("nan"), device=dev)
+    dmod_bf = ops.cast_bf16(dmod)
+    ops.gemm(dmod_bf, sc, None, out=dw, trans_a=True, trans_w=True)
+    ops.colsum(dmod, out=db)
+    assert rel_l2(dw, dmod_bf.double().t() @ sc.double()) < 1e-5   # exact products of the bf16 operands, f32 sums
+    assert rel_l2(dw, dmod.double().t() @ sc.double()) < 4e-3      # the cast of dmod is the route's only rounding
+    assert rel_l2(db, dmod.double().sum(0)) < 1e-6
+    dw2 = torch.full((R, D), float("nan"), device=dev)
+    ops.adaln_wgrad(dmod, sc, dw2)
+    assert rel_l2(dw, dw2) < 4e-3
+
+
+def test_model_gradients_with_adaln_gemm_route(dev, monkeypatch):
+    """The whole backward with the adaLN weight gradients forced through the GEMM route (what batches above 64
+    images take) against the outer-product route on the same inputs."""
+    from util import build_product_model
+
+    from fast_dit_b200 import ops as _ops
+
+    m = build_product_model("DiT-S/2", input_size=32, num_classes=1000, precision="bf16").cuda()
+    g = torch.Generator().manual_seed(12)
+    B = 8
+    x = torch.randn(B, 4, 32, 32, generator=g).cuda()
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    y = torch.randint(0, 1001, (B,), generator=g).cuda()
+    dout = torch.randn(B, 8, 32, 32, generator=g).cuda()
+    m(x, t, y).backward(dout)
+    simt = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    monkeypatch.setattr(_ops, "adaln_wgrad_preferred", lambda N, R, D: False)
+    m(x, t, y).backward(dout)
+    ada = [k for k in simt if "adaLN_modulation" in k]
+    assert len(ada) == 2 * (len(m.blocks) + 1)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_l2(p.grad, simt[k]) < (5e-3 if k in ada else 3e-3), k
+
+
 @pytest.mark.parametrize("D,T", [(384, 37), (1152, 256)])
 def test_gate_resid_bwd(ops, dev, D, T):
     g = _g(5)
