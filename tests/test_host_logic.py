@@ -236,3 +236,17 @@ def test_gemm_explicit_two_width_schedule(M, N, K, expect_table):
     assert per_pair.max() == loads[1] and loads[1] * 100 <= loads[0] * 98
     if (M, N) == (16384, 1152):
         assert n == 56 * 5 + 8 * 6 and sorted(set(per_pair.tolist())) == [4 * 360.0, 5 * 296.0]
+
+
+def test_adaln_weight_gradient_dispatch(monkeypatch):
+    """Training takes the outer-product kernel for the adaLN weight gradient up to 64 images per GPU (C4: 32) and the
+    tcgen05 GEMM over the batch above (C2: 256); shapes the kernel does not tile never take it."""
+    from fast_dit_b200 import ops
+
+    monkeypatch.delenv("DITB200_ADALN_SIMT_MAX_N", raising=False)
+    assert ops.adaln_wgrad_preferred(32, 2 * 1152, 1152) and ops.adaln_wgrad_preferred(64, 2 * 768, 768)
+    assert not ops.adaln_wgrad_preferred(65, 2 * 768, 768) and not ops.adaln_wgrad_preferred(256, 2 * 768, 768)
+    assert ops.adaln_wgrad_ok(256, 2 * 768, 768) and not ops.adaln_wgrad_ok(257, 2 * 768, 768)
+    assert not ops.adaln_wgrad_preferred(8, 2 * 200, 200)  # D not a multiple of 128
+    monkeypatch.setenv("DITB200_ADALN_SIMT_MAX_N", "256")
+    assert ops.adaln_wgrad_preferred(256, 2 * 768, 768)
