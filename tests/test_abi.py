@@ -74,3 +74,37 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_ptxas_spill_budget_of_the_hot_kernels():
+    """Build hygiene, read from the `-Xptxas -v` logs the in-tree build leaves next to the objects: every block of
+    these kernels has 10 warps, which caps them at 168 registers per thread, and what does not fit goes to local
+    memory.  The single-tile attention forward must not spill at all (its softmax loop is the kernel); the others
+    are pinned at what the measured builds had, so a change that pushes an elementwise warp into local memory — the
+    backward kernel went from 24 to 152 bytes and from 101 to 115 us when its issue loops were rewritten — fails here
+    before it costs a GPU call.  The tcgen05 GEMM's ~500 bytes sit in its register-path epilogues."""
+    import glob
+
+    import pytest
+
+    logs = glob.glob(os.path.join(ROOT, "fast_dit_b200", "lib", "obj", "*.log"))
+    if not logs:
+        pytest.skip("no ptxas logs: the library was not built in this tree")
+    spills = {}
+    for path in logs:
+        name = None
+        for line in open(path):
+            m = re.search(r"Function properties for (\S+)", line)
+            if m:
+                name = m.group(1)
+            m = re.search(r"(\d+) bytes spill stores", line)
+            if m and name:
+                spills[name] = int(m.group(1))
+    budget = {"18attn_fwd_tc_kernelE": 0, "21attn_fwd_tc_kv_kernelE": 64, "18attn_bwd_tc_kernelE": 24,
+              "14gemm_tc_kernelI": 520, "18ln_modulate_kernel": 0, "24ln_modulate_resid_kernel": 0,
+              "20p_sample_step_kernel": 0}
+    for key, limit in budget.items():
+        hit = {k: v for k, v in spills.items() if key in k}
+        assert hit, key
+        for k, v in hit.items():
+            assert v <= limit, (k, v, limit)
